@@ -1,0 +1,223 @@
+"""Host-side handle on one B200: the Python mirror of the `B200zk` wrapper in rust/ethrex-backend.
+
+One `Context` per process per GPU (the reference's prover actor runs on one
+blocking thread, `/root/reference/crates/prover/src/prover.rs:240-251`, and scales out as one process
+per GPU, `/root/reference/docs/l2/fundamentals/distributed_proving.md:36-50`).
+
+Host entry points take numpy arrays / bytes (the buffers the Rust backend would pass); device entry
+points take torch CUDA tensors, which are used only as owners of device memory and as the source of the
+current stream -- all arithmetic happens in libb200zk.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi as F
+from .errors import B200Error, NoDeviceError, status_to_error
+
+
+def _host_ptr(buf):
+    """(pointer, keepalive) for bytes / bytearray / numpy input."""
+    if isinstance(buf, np.ndarray):
+        if not buf.flags["C_CONTIGUOUS"]:
+            raise B200Error.serialization("host buffer must be C-contiguous")
+        return buf.ctypes.data_as(C.c_void_p), buf
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        return arr.ctypes.data_as(C.c_void_p), arr
+    if hasattr(buf, "data_ptr"):  # a (pinned) CPU torch tensor
+        if buf.is_cuda:
+            raise B200Error.serialization("expected a host buffer, got a CUDA tensor")
+        return C.c_void_p(buf.data_ptr()), buf
+    raise B200Error.serialization(f"unsupported host buffer type {type(buf)!r}")
+
+
+def _dev_ptr(t):
+    if not (hasattr(t, "is_cuda") and t.is_cuda):
+        raise B200Error.serialization("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise B200Error.serialization("device tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _current_stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = F.lib.b200zk_init(device, C.byref(h))
+        if rc == F.ERR_NO_DEVICE:
+            raise NoDeviceError("b200zk_init: no CUDA device -- libb200zk has no CPU fallback")
+        if rc != F.OK:
+            raise B200Error.proving(f"b200zk_init(device={device}): {F.lib.b200zk_strerror(rc).decode()}")
+        self._h = h
+        self.device = device
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            F.lib.b200zk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, what: str) -> int:
+        if rc > F.OK_INFINITY:
+            detail = F.lib.b200zk_last_error(self._h).decode(errors="replace")
+            raise status_to_error(rc, f"{what}: {F.lib.b200zk_strerror(rc).decode()} ({detail})")
+        return rc
+
+    @property
+    def launch_count(self) -> int:
+        return int(F.lib.b200zk_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(F.lib.b200zk_synchronize(self._h), "synchronize")
+
+    def set_msm_window(self, c: int):
+        self._check(F.lib.b200zk_set_msm_window(self._h, c), "set_msm_window")
+
+    def set_profiling(self, on: bool):
+        self._check(F.lib.b200zk_set_profiling(self._h, 1 if on else 0), "set_profiling")
+
+    def last_msm_phase_ms(self):
+        out = (C.c_float * 6)()
+        self._check(F.lib.b200zk_last_msm_phase_ms(self._h, out), "last_msm_phase_ms")
+        return dict(zip(("hist", "scan", "scatter", "accumulate", "bucket_reduce", "horner"), (float(x) for x in out)))
+
+    # ------------------------------------------------------------------ host-buffer entry points
+    def g1_msm(self, points, scalars, n: int, flags: int = 0) -> bytes:
+        return self._msm_host(F.lib.b200zk_g1_msm, 64, points, scalars, n, flags)
+
+    def g2_msm(self, points, scalars, n: int, flags: int = 0) -> bytes:
+        return self._msm_host(F.lib.b200zk_g2_msm, 128, points, scalars, n, flags)
+
+    def _msm_host(self, fn, out_bytes, points, scalars, n, flags):
+        pp, k1 = _host_ptr(points)
+        sp, k2 = _host_ptr(scalars)
+        out = C.create_string_buffer(out_bytes)
+        self._check(fn(self._h, pp, sp, n, flags, out), fn.__name__)
+        return out.raw
+
+    def fr_ntt(self, data, log_n: int, flags: int = 0, coset_gen: bytes | None = None):
+        """In place on a host buffer of 2^log_n 32-byte elements."""
+        dp, keep = _host_ptr(data)
+        cg = C.c_char_p(coset_gen) if coset_gen is not None else None
+        self._check(F.lib.b200zk_fr_ntt(self._h, dp, log_n, flags, C.cast(cg, C.c_void_p) if cg else None), "b200zk_fr_ntt")
+        return data
+
+    def g1_bases_upload(self, points, n: int, flags: int = 0) -> int:
+        pp, keep = _host_ptr(points)
+        h = C.c_uint64()
+        self._check(F.lib.b200zk_g1_bases_upload(self._h, pp, n, flags, C.byref(h)), "b200zk_g1_bases_upload")
+        return h.value
+
+    def g2_bases_upload(self, points, n: int, flags: int = 0) -> int:
+        pp, keep = _host_ptr(points)
+        h = C.c_uint64()
+        self._check(F.lib.b200zk_g2_bases_upload(self._h, pp, n, flags, C.byref(h)), "b200zk_g2_bases_upload")
+        return h.value
+
+    def bases_free(self, handle: int):
+        self._check(F.lib.b200zk_bases_free(self._h, handle), "b200zk_bases_free")
+
+    def g1_msm_resident(self, handle: int, scalars, n: int, flags: int = 0) -> bytes:
+        sp, keep = _host_ptr(scalars)
+        out = C.create_string_buffer(64)
+        self._check(F.lib.b200zk_g1_msm_resident(self._h, handle, sp, n, flags, out), "b200zk_g1_msm_resident")
+        return out.raw
+
+    def g2_msm_resident(self, handle: int, scalars, n: int, flags: int = 0) -> bytes:
+        sp, keep = _host_ptr(scalars)
+        out = C.create_string_buffer(128)
+        self._check(F.lib.b200zk_g2_msm_resident(self._h, handle, sp, n, flags, out), "b200zk_g2_msm_resident")
+        return out.raw
+
+    # ------------------------------------------------------------------ device-pointer entry points
+    def g1_msm_device(self, d_points, d_scalars, n: int, flags: int = 0) -> bytes:
+        out = C.create_string_buffer(64)
+        self._check(F.lib.b200zk_g1_msm_device(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), out), "b200zk_g1_msm_device")
+        return out.raw
+
+    def g2_msm_device(self, d_points, d_scalars, n: int, flags: int = 0) -> bytes:
+        out = C.create_string_buffer(128)
+        self._check(F.lib.b200zk_g2_msm_device(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), out), "b200zk_g2_msm_device")
+        return out.raw
+
+    def g1_msm_device_async(self, d_points, d_scalars, n: int, d_out, flags: int = 0):
+        self._check(F.lib.b200zk_g1_msm_device_async(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_out)), "b200zk_g1_msm_device_async")
+
+    def g2_msm_device_async(self, d_points, d_scalars, n: int, d_out, flags: int = 0):
+        self._check(F.lib.b200zk_g2_msm_device_async(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_out)), "b200zk_g2_msm_device_async")
+
+    def fr_ntt_device(self, d_data, log_n: int, flags: int = 0, coset_gen: bytes | None = None):
+        cg = C.cast(C.c_char_p(coset_gen), C.c_void_p) if coset_gen is not None else None
+        self._check(F.lib.b200zk_fr_ntt_device(self._h, _dev_ptr(d_data), log_n, flags, cg, _current_stream_ptr()), "b200zk_fr_ntt_device")
+
+    def g1_msm_partial_device(self, d_points, d_scalars, n: int, d_partial, flags: int = 0):
+        self._check(F.lib.b200zk_g1_msm_partial_device(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g1_msm_partial_device")
+
+    def g2_msm_partial_device(self, d_points, d_scalars, n: int, d_partial, flags: int = 0):
+        self._check(F.lib.b200zk_g2_msm_partial_device(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g2_msm_partial_device")
+
+    def g1_fold_partials_device(self, d_partials, count: int, flags: int = 0) -> bytes:
+        out = C.create_string_buffer(64)
+        self._check(F.lib.b200zk_g1_fold_partials_device(self._h, _dev_ptr(d_partials), count, flags, _current_stream_ptr(), out), "b200zk_g1_fold_partials_device")
+        return out.raw
+
+    def g2_fold_partials_device(self, d_partials, count: int, flags: int = 0) -> bytes:
+        out = C.create_string_buffer(128)
+        self._check(F.lib.b200zk_g2_fold_partials_device(self._h, _dev_ptr(d_partials), count, flags, _current_stream_ptr(), out), "b200zk_g2_fold_partials_device")
+        return out.raw
+
+    # ------------------------------------------------------------------ device utilities
+    def field_to_mont_device(self, d, n: int, which: int):
+        self._check(F.lib.b200zk_field_to_mont_device(self._h, _dev_ptr(d), n, which, _current_stream_ptr()), "field_to_mont")
+
+    def field_from_mont_device(self, d, n: int, which: int):
+        self._check(F.lib.b200zk_field_from_mont_device(self._h, _dev_ptr(d), n, which, _current_stream_ptr()), "field_from_mont")
+
+    def field_mul_device(self, d_a, d_b, d_out, n: int, which: int, repeat: int = 1):
+        self._check(F.lib.b200zk_field_mul_device(self._h, _dev_ptr(d_a), _dev_ptr(d_b), _dev_ptr(d_out), n, which, repeat, _current_stream_ptr()), "field_mul")
+
+    def fr_random_device(self, d_out, n: int, seed: int, start: int = 0, flags: int = 0):
+        self._check(F.lib.b200zk_fr_random_device(self._h, _dev_ptr(d_out), n, seed, start, flags, _current_stream_ptr()), "fr_random")
+
+    def g1_chain_device(self, d_out, start: int, n: int, k: int, d: int):
+        self._check(F.lib.b200zk_g1_chain_device(self._h, _dev_ptr(d_out), start, n, C.cast(C.c_char_p(k.to_bytes(32, "little")), C.c_void_p),
+                                                 C.cast(C.c_char_p(d.to_bytes(32, "little")), C.c_void_p), _current_stream_ptr()), "g1_chain")
+
+    def g2_chain_device(self, d_out, start: int, n: int, k: int, d: int):
+        self._check(F.lib.b200zk_g2_chain_device(self._h, _dev_ptr(d_out), start, n, C.cast(C.c_char_p(k.to_bytes(32, "little")), C.c_void_p),
+                                                 C.cast(C.c_char_p(d.to_bytes(32, "little")), C.c_void_p), _current_stream_ptr()), "g2_chain")
+
+    def g1_check_device(self, d_points, n: int) -> int:
+        bad = C.c_size_t()
+        rc = F.lib.b200zk_g1_check_device(self._h, _dev_ptr(d_points), n, _current_stream_ptr(), C.byref(bad))
+        if rc == F.ERR_NOT_ON_CURVE:
+            return bad.value
+        self._check(rc, "g1_check")
+        return n
+
+    def g2_check_device(self, d_points, n: int) -> int:
+        bad = C.c_size_t()
+        rc = F.lib.b200zk_g2_check_device(self._h, _dev_ptr(d_points), n, _current_stream_ptr(), C.byref(bad))
+        if rc == F.ERR_NOT_ON_CURVE:
+            return bad.value
+        self._check(rc, "g2_check")
+        return n

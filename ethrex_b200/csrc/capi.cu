@@ -1,0 +1,269 @@
+// capi.cu -- extern "C" surface of libb200zk.so (include/b200zk.h): lifecycle, host-buffer entry points,
+// resident bases, device-pointer entry points, multi-GPU partial/fold.  Style follows the in-tree C-ABI
+// precedent /root/reference/crates/guest-program/src/crypto/zisk.rs:5-64 (caller-owned buffers, small integer
+// status); the trait these calls sit behind is ProverBackend
+// (/root/reference/crates/prover/src/backend/mod.rs:81-147).
+#include "common.cuh"
+#include <cstring>
+#include <new>
+
+using namespace b200zk;
+
+namespace {
+
+template <bool G2> struct Sizes {
+  static constexpr size_t point = G2 ? 128 : 64;     // affine, native or BE
+  static constexpr size_t partial = G2 ? 256 : 128;  // XYZZ
+};
+
+int read_result(b200zk_ctx* ctx, const void* d_out, size_t bytes, cudaStream_t st, uint8_t* out) {
+  // d_out = [encoded point][u32 is_infinity]
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, d_out, bytes + 4, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(out, ctx->h_pinned, bytes);
+  uint32_t inf;
+  memcpy(&inf, ctx->h_pinned + bytes, 4);
+  return inf ? B200ZK_OK_INFINITY : B200ZK_OK;
+}
+
+template <bool G2>
+int msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_out) {
+  if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
+  B2_TRY(ensure(ctx, ctx->ws_result, 256));
+  if (G2) { B2_TRY(msm_run_g2(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p)); return msm_encode_g2(ctx, ctx->ws_result.p, 1, flags, st, d_out); }
+  B2_TRY(msm_run_g1(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p));
+  return msm_encode_g1(ctx, ctx->ws_result.p, 1, flags, st, d_out);
+}
+
+template <bool G2>
+int msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t* out) {
+  if (!ctx || !out || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
+  cudaStream_t st = pick_stream(ctx, stream);
+  B2_TRY(ensure(ctx, ctx->ws_out, 256));
+  B2_TRY(msm_device_async<G2>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p));
+  return read_result(ctx, ctx->ws_out.p, Sizes<G2>::point, st, out);
+}
+
+// scalars from host memory into ws_scalars
+int stage_scalars(b200zk_ctx* ctx, const void* scalars, size_t n, cudaStream_t st) {
+  B2_TRY(ensure(ctx, ctx->ws_scalars, n * 32 + 32));
+  if (n) B2_CUDA(ctx, cudaMemcpyAsync(ctx->ws_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+  return B200ZK_OK;
+}
+
+template <bool G2>
+int upload_points(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, cudaStream_t st, void* d_dst, DevBuf* staging) {
+  const size_t bytes = n * Sizes<G2>::point;
+  if (!n) return B200ZK_OK;
+  if (flags & B200ZK_POINTS_BE) {
+    B2_TRY(ensure(ctx, *staging, bytes));
+    B2_CUDA(ctx, cudaMemcpyAsync(staging->p, points, bytes, cudaMemcpyHostToDevice, st));
+    return points_be_to_native(ctx, staging->p, d_dst, n, G2, st);
+  }
+  B2_CUDA(ctx, cudaMemcpyAsync(d_dst, points, bytes, cudaMemcpyHostToDevice, st));
+  return B200ZK_OK;
+}
+
+template <bool G2>
+int msm_host(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t* out) {
+  if (!ctx || !out || ((!points || !scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
+  cudaStream_t st = ctx->stream;
+  B2_TRY(ensure(ctx, ctx->ws_points, n * Sizes<G2>::point + 32));
+  B2_TRY(upload_points<G2>(ctx, points, n, flags, st, ctx->ws_points.p, &ctx->ws_ntt));
+  B2_TRY(stage_scalars(ctx, scalars, n, st));
+  return msm_device<G2>(ctx, ctx->ws_points.p, ctx->ws_scalars.p, n, flags & ~B200ZK_POINTS_BE, st, out);
+}
+
+template <bool G2>
+int bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) {
+  if (!ctx || !handle || (!points && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_upload: null argument");
+  BasesEntry e;
+  e.n = n; e.g2 = G2;
+  B2_CUDA(ctx, cudaMalloc(&e.d, n * Sizes<G2>::point + 32));
+  int rc = upload_points<G2>(ctx, points, n, flags, ctx->stream, e.d, &ctx->ws_ntt);
+  if (rc > B200ZK_OK_INFINITY) { cudaFree(e.d); return rc; }
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) { cudaFree(e.d); return fail(ctx, B200ZK_ERR_CUDA, "bases upload", ce); }
+  *handle = ctx->next_handle++;
+  ctx->bases[*handle] = e;
+  return B200ZK_OK;
+}
+
+template <bool G2>
+int msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t* out) {
+  if (!ctx || !out || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: null argument");
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end() || it->second.g2 != G2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: unknown handle");
+  if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: n exceeds the resident bases");
+  B2_TRY(stage_scalars(ctx, scalars, n, ctx->stream));
+  return msm_device<G2>(ctx, it->second.d, ctx->ws_scalars.p, n, flags & ~B200ZK_POINTS_BE, ctx->stream, out);
+}
+
+template <bool G2>
+int fold_partials(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t* out) {
+  if (!ctx || !out || (!d_partials && count)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "fold_partials: null argument");
+  cudaStream_t st = pick_stream(ctx, stream);
+  B2_TRY(ensure(ctx, ctx->ws_out, 256));
+  if (G2) B2_TRY(msm_encode_g2(ctx, d_partials, count, flags, st, ctx->ws_out.p));
+  else B2_TRY(msm_encode_g1(ctx, d_partials, count, flags, st, ctx->ws_out.p));
+  return read_result(ctx, ctx->ws_out.p, Sizes<G2>::point, st, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200zk_abi_version(void) { return B200ZK_ABI_VERSION; }
+
+int b200zk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* b200zk_strerror(int status) {
+  switch (status) {
+    case B200ZK_OK: return "ok";
+    case B200ZK_OK_INFINITY: return "ok (result is the point at infinity)";
+    case B200ZK_ERR_NOT_IN_FIELD: return "input coordinate not in field";
+    case B200ZK_ERR_NOT_ON_CURVE: return "input point not on curve";
+    case B200ZK_ERR_INVALID_ARG: return "invalid argument";
+    case B200ZK_ERR_CUDA: return "CUDA error";
+    case B200ZK_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case B200ZK_ERR_OOM: return "out of device memory";
+    case B200ZK_ERR_UNSUPPORTED: return "unsupported size or option";
+    default: return "unknown status";
+  }
+}
+
+int b200zk_init(int device, b200zk_ctx** out) {
+  if (!out) return B200ZK_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = b200zk_device_count();
+  if (n <= 0) return B200ZK_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return B200ZK_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200ZK_ERR_CUDA; }
+  b200zk_ctx* ctx = new (std::nothrow) b200zk_ctx();
+  if (!ctx) return B200ZK_ERR_OOM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_pinned, 4096) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return B200ZK_ERR_CUDA;
+  }
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  *out = ctx;
+  return B200ZK_OK;
+}
+
+void b200zk_destroy(b200zk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  DevBuf* bufs[] = {&ctx->ws_hist, &ctx->ws_offsets, &ctx->ws_cursor, &ctx->ws_blocksums, &ctx->ws_idx, &ctx->ws_buckets, &ctx->ws_chunkS,
+                    &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out};
+  for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  for (auto& kv : ctx->twiddles) cudaFree(kv.second.d);
+  for (auto& kv : ctx->bases) cudaFree(kv.second.d);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* b200zk_last_error(const b200zk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int b200zk_synchronize(b200zk_ctx* ctx) {
+  if (!ctx) return B200ZK_ERR_INVALID_ARG;
+  B2_CUDA(ctx, cudaDeviceSynchronize());
+  return B200ZK_OK;
+}
+int b200zk_set_msm_window(b200zk_ctx* ctx, uint32_t c) {
+  if (!ctx || (c && (c < 2 || c > 24))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm window must be 0 or 2..24");
+  ctx->msm_window = c;
+  return B200ZK_OK;
+}
+int b200zk_set_profiling(b200zk_ctx* ctx, int enabled) {
+  if (!ctx) return B200ZK_ERR_INVALID_ARG;
+  ctx->profiling = enabled != 0;
+  return B200ZK_OK;
+}
+int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]) {
+  if (!ctx || !out_ms) return fail(ctx, B200ZK_ERR_INVALID_ARG, "phase_ms: null argument");
+  if (!ctx->profiling) return fail(ctx, B200ZK_ERR_INVALID_ARG, "profiling is off");
+  B2_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+  for (int k = 0; k < 6; ++k) B2_CUDA(ctx, cudaEventElapsedTime(&out_ms[k], ctx->ev[k], ctx->ev[k + 1]));
+  return B200ZK_OK;
+}
+
+int b200zk_g1_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t out[64]) { return msm_host<false>(ctx, points, scalars, n, flags, out); }
+int b200zk_g2_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t out[128]) { return msm_host<true>(ctx, points, scalars, n, flags, out); }
+
+int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen) {
+  if (!ctx || !data) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: null argument");
+  if (log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: log_n > 28");
+  const size_t bytes = ((size_t)1 << log_n) * 32;
+  cudaStream_t st = ctx->stream;
+  B2_TRY(ensure(ctx, ctx->ws_points, bytes));
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->ws_points.p, data, bytes, cudaMemcpyHostToDevice, st));
+  B2_TRY(ntt_run(ctx, ctx->ws_points.p, log_n, flags, coset_gen, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(data, ctx->ws_points.p, bytes, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  return B200ZK_OK;
+}
+
+int b200zk_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { return bases_upload<false>(ctx, points, n, flags, handle); }
+int b200zk_g2_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { return bases_upload<true>(ctx, points, n, flags, handle); }
+int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle) {
+  if (!ctx) return B200ZK_ERR_INVALID_ARG;
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end()) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_free: unknown handle");
+  B2_CUDA(ctx, cudaDeviceSynchronize());
+  cudaFree(it->second.d);
+  ctx->bases.erase(it);
+  return B200ZK_OK;
+}
+int b200zk_g1_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t out[64]) { return msm_resident<false>(ctx, handle, scalars, n, flags, out); }
+int b200zk_g2_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t out[128]) { return msm_resident<true>(ctx, handle, scalars, n, flags, out); }
+
+int b200zk_g1_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[64]) { return msm_device<false>(ctx, d_points, d_scalars, n, flags, stream, out); }
+int b200zk_g2_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[128]) { return msm_device<true>(ctx, d_points, d_scalars, n, flags, stream, out); }
+int b200zk_g1_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_out64) {
+  if (!ctx || !d_out64 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
+  // the encoder appends a 4-byte infinity flag: route through ws_out, then copy the point only
+  cudaStream_t st = pick_stream(ctx, stream);
+  B2_TRY(ensure(ctx, ctx->ws_out, 256));
+  B2_TRY(msm_device_async<false>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p));
+  B2_CUDA(ctx, cudaMemcpyAsync(d_out64, ctx->ws_out.p, 64, cudaMemcpyDeviceToDevice, st));
+  return B200ZK_OK;
+}
+int b200zk_g2_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_out128) {
+  if (!ctx || !d_out128 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
+  cudaStream_t st = pick_stream(ctx, stream);
+  B2_TRY(ensure(ctx, ctx->ws_out, 256));
+  B2_TRY(msm_device_async<true>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p));
+  B2_CUDA(ctx, cudaMemcpyAsync(d_out128, ctx->ws_out.p, 128, cudaMemcpyDeviceToDevice, st));
+  return B200ZK_OK;
+}
+int b200zk_fr_ntt_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, void* stream) {
+  if (!ctx || !d_data) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: null argument");
+  return ntt_run(ctx, d_data, log_n, flags, coset_gen, pick_stream(ctx, stream));
+}
+
+int b200zk_g1_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) {
+  if (!ctx || !d_partial128 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial: null argument");
+  if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
+  return msm_run_g1(ctx, d_points, d_scalars, n, flags, pick_stream(ctx, stream), d_partial128);
+}
+int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
+  if (!ctx || !d_partial256 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial: null argument");
+  if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
+  return msm_run_g2(ctx, d_points, d_scalars, n, flags, pick_stream(ctx, stream), d_partial256);
+}
+int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[64]) { return fold_partials<false>(ctx, d_partials, count, flags, stream, out); }
+int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[128]) { return fold_partials<true>(ctx, d_partials, count, flags, stream, out); }
+
+}  // extern "C"

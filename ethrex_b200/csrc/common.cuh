@@ -1,0 +1,154 @@
+// common.cuh -- context, workspace and launch bookkeeping shared by the translation units of libb200zk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+#include "curve.cuh"
+
+namespace b200zk {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct TwiddleSet {   // per (log_n, direction): see ntt.cu
+  void* d = nullptr;  // device allocation holding all tables
+  size_t bytes = 0;
+};
+
+struct BasesEntry {
+  void* d = nullptr;
+  size_t n = 0;
+  bool g2 = false;
+};
+
+}  // namespace b200zk
+
+struct b200zk_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  uint64_t launches = 0;
+  uint32_t msm_window = 0;
+  bool profiling = false;
+  float phase_ms[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[8] = {};
+  // grow-only workspaces
+  b200zk::DevBuf ws_hist, ws_offsets, ws_cursor, ws_blocksums, ws_idx, ws_buckets, ws_chunkS, ws_chunkV, ws_result,
+      ws_points, ws_scalars, ws_ntt, ws_misc, ws_out;
+  std::map<uint64_t, b200zk::TwiddleSet> twiddles;
+  std::map<uint64_t, b200zk::BasesEntry> bases;
+  uint64_t next_handle = 1;
+  uint8_t* h_pinned = nullptr;  // 4 KiB pinned staging for results / flags
+};
+
+namespace b200zk {
+
+inline int fail(b200zk_ctx* ctx, int status, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    ctx->last_error = what;
+    if (e != cudaSuccess) { ctx->last_error += ": "; ctx->last_error += cudaGetErrorString(e); }
+  }
+  return status;
+}
+
+#define B2_CUDA(ctx, expr)                                                      \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) return b200zk::fail(ctx, _e == cudaErrorMemoryAllocation ? B200ZK_ERR_OOM : B200ZK_ERR_CUDA, #expr, _e); \
+  } while (0)
+
+#define B2_TRY(expr)                        \
+  do {                                      \
+    int _s = (expr);                        \
+    if (_s > B200ZK_OK_INFINITY) return _s; \
+  } while (0)
+
+inline int ensure(b200zk_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return B200ZK_OK;
+  // never free a buffer that queued kernels may still read
+  B2_CUDA(ctx, cudaDeviceSynchronize());
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&b.p, want); }
+  if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(ctx, B200ZK_ERR_OOM, "cudaMalloc workspace", e); }
+  b.cap = want;
+  return B200ZK_OK;
+}
+
+inline cudaStream_t pick_stream(b200zk_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+// every kernel launch in the library goes through this macro so gpu_launches is a count, not a guess
+#define B2_LAUNCH(ctx, kernel, grid, block, smem, st, ...)                                   \
+  do {                                                                                       \
+    kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                                  \
+    (ctx)->launches++;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) return b200zk::fail(ctx, B200ZK_ERR_CUDA, "launch " #kernel, _e); \
+  } while (0)
+
+// 32-byte element as two 128-bit words: every field element moves through HBM as LDG.128/STG.128 pairs
+template <class F> B2_D F load_fe(const void* base, size_t index) {
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * index;
+  uint4 lo = p[0], hi = p[1];
+  F r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+template <class F> B2_D F load_fe_nc(const void* base, size_t index) {  // read-only path
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 2 * index;
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  F r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+template <class F> B2_D void store_fe(void* base, size_t index, const F& a) {
+  uint4* p = reinterpret_cast<uint4*>(base) + 2 * index;
+  p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  p[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+// field-generic element I/O at "slot" granularity: slot = index of a 32-byte word
+B2_D Fq load_field(const void* base, size_t slot, const Fq*) { return load_fe<Fq>(base, slot); }
+B2_D Fq2 load_field(const void* base, size_t slot, const Fq2*) { return {load_fe<Fq>(base, 2 * slot), load_fe<Fq>(base, 2 * slot + 1)}; }
+B2_D Fq load_field_nc(const void* base, size_t slot, const Fq*) { return load_fe_nc<Fq>(base, slot); }
+B2_D Fq2 load_field_nc(const void* base, size_t slot, const Fq2*) { return {load_fe_nc<Fq>(base, 2 * slot), load_fe_nc<Fq>(base, 2 * slot + 1)}; }
+B2_D void store_field(void* base, size_t slot, const Fq& a) { store_fe<Fq>(base, slot, a); }
+B2_D void store_field(void* base, size_t slot, const Fq2& a) { store_fe<Fq>(base, 2 * slot, a.c0); store_fe<Fq>(base, 2 * slot + 1, a.c1); }
+
+template <class F> B2_D Affine<F> load_affine_nc(const void* base, size_t i) {
+  return {load_field_nc(base, 2 * i, (const F*)nullptr), load_field_nc(base, 2 * i + 1, (const F*)nullptr)};
+}
+template <class F> B2_D void store_affine(void* base, size_t i, const Affine<F>& p) {
+  store_field(base, 2 * i, p.x); store_field(base, 2 * i + 1, p.y);
+}
+template <class F> B2_D XYZZ<F> load_xyzz(const void* base, size_t i) {
+  const F* t = nullptr;
+  return {load_field(base, 4 * i, t), load_field(base, 4 * i + 1, t), load_field(base, 4 * i + 2, t), load_field(base, 4 * i + 3, t)};
+}
+template <class F> B2_D void store_xyzz(void* base, size_t i, const XYZZ<F>& p) {
+  store_field(base, 4 * i, p.x); store_field(base, 4 * i + 1, p.y); store_field(base, 4 * i + 2, p.zz); store_field(base, 4 * i + 3, p.zzz);
+}
+template <class F> struct FieldBytes;
+template <> struct FieldBytes<Fq> { static constexpr size_t value = 32; };
+template <> struct FieldBytes<Fq2> { static constexpr size_t value = 64; };
+
+// internal cross-TU entry points
+int msm_run_g1(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial);
+int msm_run_g2(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial);
+int msm_encode_g1(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, cudaStream_t st, void* d_out);
+int msm_encode_g2(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, cudaStream_t st, void* d_out);
+int points_be_to_native(b200zk_ctx* ctx, const void* d_be, void* d_native, size_t n, bool g2, cudaStream_t st);
+int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st);
+
+}  // namespace b200zk

@@ -1,0 +1,355 @@
+// msm.cu -- windowed Pippenger multi-scalar multiplication over BN254 G1 / G2 for sm_100a.
+//
+// Replaces ark_ec::VariableBaseMSM::msm (ark-ec 0.5.0, /root/reference/Cargo.lock:978) as reached by the
+// Groth16 wrap behind /root/reference/crates/prover/src/backend/sp1.rs:97-134 and risc0.rs:24-29,71-82
+// (SURVEY.md section 8a rows a6/a7).  Same digit rule as ark's `make_digits` (signed radix-2^c digits, carry
+// when the window value >= 2^(c-1), 2^(c-1) buckets per window), but the schedule is GPU shaped:
+//
+//   1. msm_hist      one thread per scalar: recode into W signed digits, histogram (window,bucket) with
+//                    spread global atomics (the W*2^(c-1) counters live in L2);
+//   2. scan_*        exclusive prefix sum of the histogram -> bucket offsets (3 small kernels);
+//   3. msm_scatter   recode again (cheaper than storing n*W digits) and drop each point index, with the
+//                    digit's sign in bit 31, into its bucket's slice of the sorted index array;
+//   4. msm_accumulate  THE hot kernel: one thread per bucket walks its slice, gathers 64/128-byte affine
+//                    bases with 128-bit loads and folds them into an XYZZ accumulator (8M+2S per point);
+//   5. bucket_chunk / bucket_tree  sum_b (b+1)*B_b per window: running sums over chunks of 32 buckets, then a
+//                    log-depth pairwise tree carrying (sum, weighted sum) -- no serial 2^(c-1) loop anywhere;
+//   6. msm_horner    sum_w 2^(c*w) * S_w in one thread (W*c doublings), leaving one XYZZ partial sum.
+//
+// The affine normalisation / byte encoding (msm_encode) is a separate single-thread kernel so that the
+// multi-GPU path can all-gather the 128/256-byte XYZZ partials first.
+#include "common.cuh"
+
+namespace b200zk {
+
+static constexpr int kMaxWindows = 64;
+static constexpr int kChunk = 32;  // buckets per running-sum chunk
+
+struct MsmPlan {
+  uint32_t c, W, B;       // window bits, windows, buckets per window (2^(c-1))
+  uint32_t chunk, T;      // buckets per chunk, chunks per window
+};
+
+static MsmPlan make_plan(size_t n, uint32_t forced_c) {
+  uint32_t lg = 0;
+  while (((size_t)1 << lg) < n) ++lg;
+  uint32_t c = forced_c ? forced_c : (lg > 8 ? lg - 4 : 4);
+  if (!forced_c && c > 20) c = 20;
+  if (c < 2) c = 2;
+  if (c > 24) c = 24;
+  MsmPlan p;
+  p.c = c;
+  p.W = (255 + c - 1) / c;
+  p.B = 1u << (c - 1);
+  p.chunk = p.B < (uint32_t)kChunk ? p.B : (uint32_t)kChunk;
+  p.T = p.B / p.chunk;
+  return p;
+}
+
+// ---- scalar loading and signed-digit recoding -----------------------------------------------------------
+B2_D void load_scalar(const void* scalars, size_t i, uint32_t flags, uint32_t s[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * i;
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  if (flags & B200ZK_SCALARS_BE) {
+    s[7] = __byte_perm(lo.x, 0, 0x0123); s[6] = __byte_perm(lo.y, 0, 0x0123); s[5] = __byte_perm(lo.z, 0, 0x0123); s[4] = __byte_perm(lo.w, 0, 0x0123);
+    s[3] = __byte_perm(hi.x, 0, 0x0123); s[2] = __byte_perm(hi.y, 0, 0x0123); s[1] = __byte_perm(hi.z, 0, 0x0123); s[0] = __byte_perm(hi.w, 0, 0x0123);
+  } else {
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+  }
+  Fr f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f.v[k] = s[k];
+  if (flags & B200ZK_SCALARS_MONT) {
+    // a Montgomery residue may be any value < 2^256 only if malformed; reduce first so mul's bound holds
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+      Fr m = Fr::modulus(), t; uint32_t borrow = detail::sub8(t.v, f.v, m.v);
+      if (!borrow) f = t;
+    }
+    f = Fr::from_mont(f);
+  } else {
+    // 2^256 / r < 6: at most five subtractions bring any 256-bit value below r
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+      Fr m = Fr::modulus(), t; uint32_t borrow = detail::sub8(t.v, f.v, m.v);
+      if (!borrow) f = t;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = f.v[k];
+}
+
+// window w of the 256-bit scalar, c <= 24 bits
+B2_D uint32_t window_bits(const uint32_t s[8], uint32_t w, uint32_t c) {
+  uint32_t bit = w * c;
+  uint32_t limb = bit >> 5, off = bit & 31;
+  if (limb >= 8) return 0;
+  uint64_t v = s[limb];
+  if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+  return (uint32_t)(v >> off) & ((1u << c) - 1u);
+}
+
+// Calls f(w, bucket_index_0based, negative) for every non-zero signed digit of the scalar.
+template <class Fn> B2_D void for_each_digit(const uint32_t s[8], const MsmPlan& pl, Fn f) {
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < pl.W; ++w) {
+    uint32_t coef = window_bits(s, w, pl.c) + carry;
+    carry = 0;
+    bool neg = false;
+    uint32_t mag = coef;
+    if (w + 1 < pl.W && coef >= pl.B) {  // ark make_digits: carry = (coef + radix/2) >> c
+      carry = 1; neg = true; mag = (1u << pl.c) - coef;
+    }
+    if (mag) f(w, mag - 1, neg);
+  }
+}
+
+__global__ void __launch_bounds__(256) msm_hist(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* hist) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t s[8];
+    load_scalar(scalars, i, flags, s);
+    for_each_digit(s, pl, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&hist[(size_t)w * pl.B + b], 1u); });
+  }
+}
+
+__global__ void __launch_bounds__(256) msm_scatter(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* cursor, uint32_t* idx) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t s[8];
+    load_scalar(scalars, i, flags, s);
+    for_each_digit(s, pl, [&](uint32_t w, uint32_t b, bool neg) {
+      uint32_t pos = atomicAdd(&cursor[(size_t)w * pl.B + b], 1u);
+      idx[pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+    });
+  }
+}
+
+// ---- exclusive scan of the histogram (G entries) ---------------------------------------------------------
+static constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, size_t G, uint32_t* tile_sums) {
+  __shared__ uint32_t red[kScanThreads / 32];
+  size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += in[base + k];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int k = 0; k < kScanThreads / 32; ++k) t += red[k];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) scan_tile_offsets(uint32_t* tile_sums, size_t tiles) {
+  // single block: exclusive scan of up to a few thousand tile sums, 1024 at a time
+  __shared__ uint32_t buf[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < tiles; base += 1024) {
+    size_t i = base + threadIdx.x;
+    uint32_t v = i < tiles ? tile_sums[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t t = threadIdx.x >= (unsigned)o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint32_t incl = buf[threadIdx.x], c0 = carry;
+    __syncthreads();
+    if (i < tiles) tile_sums[i] = c0 + incl - v;
+    if (threadIdx.x == 1023) carry = c0 + incl;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, size_t G, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
+  size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? in[base + k] : 0; s += v[k]; }
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += t; }
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (unsigned k = 0; k < (threadIdx.x >> 5); ++k) wbase += warp_tot[k];
+  uint32_t run = tile_offsets[blockIdx.x] + wbase + incl - s;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < G) { offsets[base + k] = run; cursor[base + k] = run; }
+    run += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) offsets[G] = run;  // total
+}
+
+// ---- bucket accumulation ----------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
+                                                      const uint32_t* __restrict__ offsets, size_t G, void* __restrict__ buckets) {
+  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  uint32_t lo = offsets[g], hi = offsets[g + 1];
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (uint32_t e = lo; e < hi; ++e) {
+    uint32_t v = __ldg(idx + e);
+    Affine<F> p = load_affine_nc<F>(points, v & 0x7fffffffu);
+    if (v >> 31) p.y = F::neg(p.y);
+    xyzz_add_mixed(acc, p.x, p.y);
+  }
+  store_xyzz(buckets, g, acc);
+}
+
+// ---- bucket reduction: S_w = sum_b (b+1) * B[w][b] ---------------------------------------------------------
+// chunk j of window w: S = sum B, V = sum_k (k+1) * B[j*chunk + k]
+template <class F>
+__global__ void __launch_bounds__(128) bucket_chunk(const void* __restrict__ buckets, MsmPlan pl, void* __restrict__ chunkS, void* __restrict__ chunkV) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t total = (size_t)pl.W * pl.T;
+  if (t >= total) return;
+  size_t first = t * pl.chunk;  // bucket arrays are [w][b] contiguous and T*chunk == B
+  XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+  for (int k = (int)pl.chunk - 1; k >= 0; --k) {
+    XYZZ<F> b = load_xyzz<F>(buckets, first + k);
+    xyzz_add(run, b);
+    xyzz_add(acc, run);
+  }
+  store_xyzz(chunkS, t, run);
+  store_xyzz(chunkV, t, acc);
+}
+// one tree level: node j (multiple of 2*half) absorbs node j+half; the right block starts `half` chunks =
+// half*chunk buckets later, so V += V_r + (half*chunk) * S_r  (a power of two: log2 doublings)
+template <class F>
+__global__ void __launch_bounds__(128) bucket_tree(MsmPlan pl, uint32_t half, uint32_t shift_log2, void* __restrict__ chunkS, void* __restrict__ chunkV) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  uint32_t pairs = pl.T / (2 * half);
+  if (t >= (size_t)pl.W * pairs) return;
+  size_t w = t / pairs, j = (t % pairs) * 2 * half;
+  size_t left = w * pl.T + j, right = left + half;
+  XYZZ<F> Sl = load_xyzz<F>(chunkS, left), Sr = load_xyzz<F>(chunkS, right);
+  XYZZ<F> Vl = load_xyzz<F>(chunkV, left), Vr = load_xyzz<F>(chunkV, right);
+  xyzz_add(Vl, Vr);
+  xyzz_add(Sl, Sr);
+  for (uint32_t k = 0; k < shift_log2; ++k) Sr = xyzz_dbl(Sr);
+  xyzz_add(Vl, Sr);
+  store_xyzz(chunkS, left, Sl);
+  store_xyzz(chunkV, left, Vl);
+}
+// Horner over the window sums (chunkV[w*T] after the tree): result = sum_w 2^(c*w) * S_w
+template <class F>
+__global__ void msm_horner(MsmPlan pl, const void* __restrict__ chunkV, void* __restrict__ result) {
+  if (blockIdx.x || threadIdx.x) return;
+  XYZZ<F> acc = load_xyzz<F>(chunkV, (size_t)(pl.W - 1) * pl.T);
+  for (int w = (int)pl.W - 2; w >= 0; --w) {
+    for (uint32_t k = 0; k < pl.c; ++k) acc = xyzz_dbl(acc);
+    XYZZ<F> s = load_xyzz<F>(chunkV, (size_t)w * pl.T);
+    xyzz_add(acc, s);
+  }
+  store_xyzz(result, 0, acc);
+}
+template <class F> __global__ void write_identity(void* result) {
+  if (blockIdx.x || threadIdx.x) return;
+  store_xyzz(result, 0, XYZZ<F>::identity());
+}
+
+// ---- fold partials, normalise, encode ----------------------------------------------------------------------
+B2_D void store_be32(uint8_t* out, const Fq& canonical) {
+  uint32_t* o = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = __byte_perm(canonical.v[7 - k], 0, 0x0123);
+}
+B2_D void encode_point(uint8_t* out, const Affine<Fq>& p, bool native) {
+  if (native) { store_affine<Fq>(out, 0, p); return; }
+  store_be32(out, Fq::from_mont(p.x)); store_be32(out + 32, Fq::from_mont(p.y));
+}
+B2_D void encode_point(uint8_t* out, const Affine<Fq2>& p, bool native) {
+  if (native) { store_affine<Fq2>(out, 0, p); return; }
+  // EIP-197 order x_im | x_re | y_im | y_re (provider.rs:307-320)
+  store_be32(out, Fq::from_mont(p.x.c1)); store_be32(out + 32, Fq::from_mont(p.x.c0));
+  store_be32(out + 64, Fq::from_mont(p.y.c1)); store_be32(out + 96, Fq::from_mont(p.y.c0));
+}
+// d_out layout: [encoded point (64 or 128 B)] [uint32 is_infinity]
+template <class F>
+__global__ void msm_encode(const void* __restrict__ partials, size_t count, bool native, uint8_t* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (size_t k = 0; k < count; ++k) { XYZZ<F> p = load_xyzz<F>(partials, k); xyzz_add(acc, p); }
+  Affine<F> a = xyzz_to_affine(acc);
+  encode_point(out, a, native);
+  *reinterpret_cast<uint32_t*>(out + 4 * FieldBytes<F>::value) = a.is_inf() ? 1u : 0u;
+}
+
+// ---- host orchestration ---------------------------------------------------------------------------------------
+static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
+  if (ctx->profiling) cudaEventRecord(ctx->ev[k], st);
+}
+
+template <class F>
+static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial) {
+  if (n == 0) {
+    B2_LAUNCH(ctx, write_identity<F>, 1, 32, 0, st, d_partial);
+    return B200ZK_OK;
+  }
+  if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+  const MsmPlan pl = make_plan(n, ctx->msm_window);
+  const size_t G = (size_t)pl.W * pl.B;
+  const size_t tiles = (G + kScanTile - 1) / kScanTile;
+  const size_t xy = 4 * FieldBytes<F>::value;
+  B2_TRY(ensure(ctx, ctx->ws_hist, G * 4));
+  B2_TRY(ensure(ctx, ctx->ws_offsets, (G + 1) * 4));
+  B2_TRY(ensure(ctx, ctx->ws_cursor, G * 4));
+  B2_TRY(ensure(ctx, ctx->ws_blocksums, tiles * 4));
+  B2_TRY(ensure(ctx, ctx->ws_idx, n * (size_t)pl.W * 4));
+  B2_TRY(ensure(ctx, ctx->ws_buckets, G * xy));
+  B2_TRY(ensure(ctx, ctx->ws_chunkS, (size_t)pl.W * pl.T * xy));
+  B2_TRY(ensure(ctx, ctx->ws_chunkV, (size_t)pl.W * pl.T * xy));
+  uint32_t* hist = (uint32_t*)ctx->ws_hist.p;
+  uint32_t* offsets = (uint32_t*)ctx->ws_offsets.p;
+  uint32_t* cursor = (uint32_t*)ctx->ws_cursor.p;
+  uint32_t* tsum = (uint32_t*)ctx->ws_blocksums.p;
+  uint32_t* idx = (uint32_t*)ctx->ws_idx.p;
+
+  phase_mark(ctx, 0, st);
+  B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
+  const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+  B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist);
+  phase_mark(ctx, 1, st);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, G, tsum);
+  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, G, tsum, offsets, cursor);
+  phase_mark(ctx, 2, st);
+  B2_LAUNCH(ctx, msm_scatter, sgrid, 256, 0, st, d_scalars, n, flags, pl, cursor, idx);
+  phase_mark(ctx, 3, st);
+  B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((G + 127) / 128), 128, 0, st, d_points, idx, offsets, G, ctx->ws_buckets.p);
+  phase_mark(ctx, 4, st);
+  const size_t chunks = (size_t)pl.W * pl.T;
+  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  uint32_t chunk_log2 = 0;
+  while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
+  for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
+    size_t pairs = (size_t)pl.W * (pl.T / (2 * half));
+    B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  }
+  phase_mark(ctx, 5, st);
+  B2_LAUNCH(ctx, msm_horner<F>, 1, 32, 0, st, pl, ctx->ws_chunkV.p, d_partial);
+  phase_mark(ctx, 6, st);
+  return B200ZK_OK;
+}
+
+template <class F>
+static int msm_encode_host(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, cudaStream_t st, void* d_out) {
+  B2_LAUNCH(ctx, msm_encode<F>, 1, 32, 0, st, d_partials, count, (flags & B200ZK_OUT_NATIVE) != 0, (uint8_t*)d_out);
+  return B200ZK_OK;
+}
+
+int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out) { return msm_run<Fq>(ctx, p, s, n, f, st, out); }
+int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out) { return msm_run<Fq2>(ctx, p, s, n, f, st, out); }
+int msm_encode_g1(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq>(ctx, p, c, f, st, out); }
+int msm_encode_g2(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq2>(ctx, p, c, f, st, out); }
+
+}  // namespace b200zk

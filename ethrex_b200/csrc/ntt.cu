@@ -1,0 +1,328 @@
+// ntt.cu -- number-theoretic transform over the BN254 scalar field Fr for sm_100a.
+//
+// Replaces ark_poly::Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place (ark-poly 0.5.0,
+// /root/reference/Cargo.lock:1140; equal to gnark-crypto bn254 fr/fft) as used by the Groth16 wrap behind
+// /root/reference/crates/prover/src/backend/sp1.rs:97-134.
+//   out[k] = sum_j a[j] * w^(jk),  natural order in and out,  w = g^(2^(28-log_n)),  g = 5^((r-1)/2^28).
+//
+// Schedule: merged-stage Cooley-Tukey in Stockham (auto-sort) form.  log_n stages are split into P passes
+// of s_p stages; pass p with Ns = prod_{q<p} 2^(s_q) and R = 2^(s_p) computes, for every j in [0, N/R):
+//     v[r]  = in[j + r*N/R] * w_N^( r * (j mod Ns) * N/(Ns*R) )          (inter-pass twiddle)
+//     V     = NTT_R(v)                                                     (s_p radix-2 stages in shared memory)
+//     out[(j div Ns)*Ns*R + (j mod Ns) + q*Ns] = V[q]
+// One CTA owns a tile of 2^t adjacent j, so every global access is a run of 2^t * 32 B, and the R-point
+// transforms of a tile never leave shared memory.  Inter-pass twiddles come from two 4096-entry tables
+// (w^lo, w^(hi*4096)): one extra multiplication instead of an n/2-entry table streamed from HBM.
+#include "common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace b200zk {
+
+static constexpr int kLoBits = 12;
+static constexpr int kMaxStage = 12;  // 2^12 elements * 32 B = 128 KiB of shared memory
+
+// device table layout (in Fr elements)
+struct NttTables {
+  const uint4* stage;  // stage[(2^(s-1) - 1) + i] = w_{2^s}^i, s = 1..12
+  const uint4* lo;     // lo[x] = w_N^x, x < 2^min(12, k)
+  const uint4* hi;     // hi[y] = w_N^(y << 12)
+  const uint4* ninv;   // n^-1
+};
+
+B2_D Fr fr_root_2_28() {  // 5^((r-1)/2^28), canonical 0x2a3c09f0a58a7e85...725b19f0
+  const uint32_t g[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+  Fr c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c.v[i] = g[i];
+  return Fr::to_mont(c);
+}
+B2_D Fr fr_pow_u32(Fr b, uint32_t e) {
+  Fr acc = Fr::one();
+  while (e) { if (e & 1) acc = Fr::mul(acc, b); b = Fr::sqr(b); e >>= 1; }
+  return acc;
+}
+B2_D Fr root_of_unity(uint32_t log_n) {
+  Fr w = fr_root_2_28();
+  for (uint32_t i = log_n; i < 28; ++i) w = Fr::sqr(w);
+  return w;
+}
+
+// entries: [0, 4095) stage tables, then 2^lb lo, then 2^(k-lb) hi, then n^-1
+__global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inverse, void* out, uint32_t n_lo, uint32_t n_hi) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_stage = (1u << kMaxStage) - 1;
+  uint32_t total = n_stage + n_lo + n_hi + 1;
+  if (id >= total) return;
+  Fr val;
+  if (id < n_stage) {
+    uint32_t s = 32 - __clz(id + 1);           // id+1 in [2^(s-1), 2^s)
+    uint32_t i = id + 1 - (1u << (s - 1));
+    Fr w = root_of_unity(s);
+    uint32_t e = inverse ? ((1u << s) - i) & ((1u << s) - 1) : i;
+    val = fr_pow_u32(w, e);
+  } else if (id < n_stage + n_lo + n_hi) {
+    uint32_t x = id - n_stage;
+    uint32_t e = x < n_lo ? x : (x - n_lo) << kLoBits;
+    uint32_t N = 1u << log_n;  // log_n <= 28
+    if (inverse) e = (N - e) & (N - 1);
+    val = fr_pow_u32(root_of_unity(log_n), e);
+  } else {
+    Fr n = Fr::zero(); n.v[0] = 1u << log_n;
+    val = inverse ? Fr::inv(Fr::to_mont(n)) : Fr::one();
+  }
+  store_fe<Fr>(out, id, val);
+}
+
+struct PassArgs {
+  const void* in;
+  void* out;
+  uint32_t log_n, s, t, log_ns;
+  uint32_t scale_out;  // multiply outputs by n^-1
+  NttTables tb;
+};
+
+B2_D Fr lds_fr(const uint4* sm, uint32_t i) {
+  uint4 lo = sm[2 * i], hi = sm[2 * i + 1];
+  Fr r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+B2_D void sts_fr(uint4* sm, uint32_t i, const Fr& a) {
+  sm[2 * i] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  sm[2 * i + 1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
+  extern __shared__ uint4 sm[];
+  const uint32_t k = a.log_n, s = a.s, t = a.t, lns = a.log_ns;
+  const uint32_t R = 1u << s, cols = 1u << t, cmask = cols - 1;
+  const uint32_t ns_mask = (1u << lns) - 1;
+  const uint32_t stride_log = k - s;                         // N/R
+  const uint32_t j0 = blockIdx.x << t;
+  const uint32_t items = R << t;
+
+  // ---- load (+ inter-pass twiddle) : item -> (r, c), c fastest => 2^t * 32 B runs
+  for (uint32_t it = threadIdx.x; it < items; it += THREADS) {
+    uint32_t c = it & cmask, r = it >> t;
+    uint32_t j = j0 + c;
+    Fr v = load_fe<Fr>(a.in, (size_t)j + ((size_t)r << stride_log));
+    if (lns) {
+      uint32_t e = (r * (j & ns_mask)) << (k - lns - s);
+      Fr tw = load_fe_nc<Fr>(a.tb.lo, e & ((1u << kLoBits) - 1));
+      if (k > (uint32_t)kLoBits) tw = Fr::mul(tw, load_fe_nc<Fr>(a.tb.hi, e >> kLoBits));
+      v = Fr::mul(v, tw);
+    }
+    sts_fr(sm, it, v);  // sm[(r << t) + c]
+  }
+  __syncthreads();
+
+  // ---- s decimation-in-frequency stages in shared memory
+  const uint4* stage_tw = a.tb.stage + 2 * ((size_t)(R >> 1) - 1);
+  const uint32_t half_items = items >> 1;
+  for (uint32_t q = 0; q < s; ++q) {
+    const uint32_t lm = s - 1 - q, m = 1u << lm;
+    for (uint32_t it = threadIdx.x; it < half_items; it += THREADS) {
+      uint32_t c = it & cmask, bf = it >> t;
+      uint32_t jj = bf & (m - 1);
+      uint32_t i = ((bf >> lm) << (lm + 1)) | jj;
+      uint32_t p0 = (i << t) + c, p1 = ((i + m) << t) + c;
+      Fr x = lds_fr(sm, p0), y = lds_fr(sm, p1);
+      Fr d = Fr::sub(x, y);
+      if (m > 1) d = Fr::mul(d, load_fe_nc<Fr>(stage_tw, jj << q));
+      sts_fr(sm, p0, Fr::add(x, y));
+      sts_fr(sm, p1, d);
+    }
+    __syncthreads();
+  }
+
+  // ---- store: V[q] sits at bit-reversed row brev_s(q)
+  const Fr ninv = a.scale_out ? load_fe_nc<Fr>(a.tb.ninv, 0) : Fr::one();
+  if (lns == 0) {
+    // first pass: out[j*R + q], q fastest => the tile is one contiguous run of R * 2^t elements
+    for (uint32_t it = threadIdx.x; it < items; it += THREADS) {
+      uint32_t q = it & (R - 1), c = it >> s;
+      uint32_t row = s ? (__brev(q) >> (32 - s)) : 0;
+      Fr v = lds_fr(sm, (row << t) + c);
+      if (a.scale_out) v = Fr::mul(v, ninv);
+      store_fe<Fr>(a.out, (((size_t)(j0 + c)) << s) + q, v);
+    }
+  } else {
+    for (uint32_t it = threadIdx.x; it < items; it += THREADS) {
+      uint32_t c = it & cmask, q = it >> t;
+      uint32_t row = s ? (__brev(q) >> (32 - s)) : 0;
+      uint32_t j = j0 + c;
+      Fr v = lds_fr(sm, (row << t) + c);
+      if (a.scale_out) v = Fr::mul(v, ninv);
+      size_t o = (((size_t)(j >> lns)) << (lns + s)) + (j & ns_mask) + ((size_t)q << lns);
+      store_fe<Fr>(a.out, o, v);
+    }
+  }
+}
+
+// data[i] *= hi[i >> 12] * lo[i & 4095]   (coset shift h^i, or h^-i * n^-1)
+__global__ void __launch_bounds__(256) ntt_scale_pow(void* data, size_t n, const void* lo, const void* hi, int has_hi) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr tw = load_fe_nc<Fr>(lo, i & ((1u << kLoBits) - 1));
+    if (has_hi) tw = Fr::mul(tw, load_fe_nc<Fr>(hi, i >> kLoBits));
+    store_fe<Fr>(data, i, Fr::mul(load_fe<Fr>(data, i), tw));
+  }
+}
+// lo[x] = base^x * scale (x < n_lo), hi[y] = base^(y << 12) (y < n_hi); base given canonical
+__global__ void __launch_bounds__(128) ntt_build_pow_tables(const uint32_t* base_canonical, int invert, int scale_ninv, uint32_t log_n, void* lo, uint32_t n_lo, void* hi, uint32_t n_hi) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_lo + n_hi) return;
+  Fr b;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b.v[i] = base_canonical[i];
+  b = Fr::to_mont(b);
+  if (invert) b = Fr::inv(b);
+  if (id < n_lo) {
+    Fr v = fr_pow_u32(b, id);
+    if (scale_ninv) { Fr n = Fr::zero(); n.v[0] = 1u << log_n; v = Fr::mul(v, Fr::inv(Fr::to_mont(n))); }
+    store_fe<Fr>(lo, id, v);
+  } else {
+    store_fe<Fr>(hi, id - n_lo, fr_pow_u32(b, (id - n_lo) << kLoBits));
+  }
+}
+
+// canonical <-> Montgomery (+ optional byte order), in place
+__global__ void __launch_bounds__(256) fr_convert(void* data, size_t n, int to_mont, int big_endian) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v = load_fe<Fr>(data, i);
+    if (to_mont) {
+      if (big_endian) { Fr w; for (int k = 0; k < 8; ++k) w.v[k] = __byte_perm(v.v[7 - k], 0, 0x0123); v = w; }
+      for (int k = 0; k < 5; ++k) { Fr m = Fr::modulus(), tt; if (!detail::sub8(tt.v, v.v, m.v)) v = tt; }
+      v = Fr::to_mont(v);
+    } else {
+      v = Fr::from_mont(v);
+      if (big_endian) { Fr w; for (int k = 0; k < 8; ++k) w.v[k] = __byte_perm(v.v[7 - k], 0, 0x0123); v = w; }
+    }
+    store_fe<Fr>(data, i, v);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_t st, NttTables* out) {
+  const uint64_t key = (uint64_t)log_n | ((uint64_t)inverse << 8);
+  const uint32_t n_stage = (1u << kMaxStage) - 1;
+  const uint32_t lb = log_n < (uint32_t)kLoBits ? log_n : (uint32_t)kLoBits;
+  const uint32_t n_lo = 1u << lb, n_hi = log_n > (uint32_t)kLoBits ? 1u << (log_n - kLoBits) : 1u;
+  auto it = ctx->twiddles.find(key);
+  if (it == ctx->twiddles.end()) {
+    TwiddleSet ts;
+    ts.bytes = (size_t)(n_stage + n_lo + n_hi + 1) * 32;
+    B2_CUDA(ctx, cudaMalloc(&ts.d, ts.bytes));
+    uint32_t total = n_stage + n_lo + n_hi + 1;
+    B2_LAUNCH(ctx, ntt_build_tables, (total + 127) / 128, 128, 0, st, log_n, inverse ? 1 : 0, ts.d, n_lo, n_hi);
+    it = ctx->twiddles.emplace(key, ts).first;
+  }
+  const uint4* base = (const uint4*)it->second.d;
+  out->stage = base;
+  out->lo = base + 2 * (size_t)n_stage;
+  out->hi = out->lo + 2 * (size_t)n_lo;
+  out->ninv = out->hi + 2 * (size_t)n_hi;
+  return B200ZK_OK;
+}
+
+struct Plan { int P; uint32_t s[4]; uint32_t t[4]; };
+
+static Plan make_ntt_plan(uint32_t k) {
+  Plan p{};
+  const char* env = getenv("B200ZK_NTT_PLAN");  // e.g. "8,8,8" : experiment knob
+  if (env && *env) {
+    uint32_t sum = 0; int P = 0; const char* c = env;
+    while (*c && P < 4) { p.s[P] = (uint32_t)strtoul(c, (char**)&c, 10); sum += p.s[P]; ++P; if (*c == ',') ++c; }
+    bool ok = sum == k;
+    for (int i = 0; i < P; ++i) ok = ok && p.s[i] >= 1 && p.s[i] <= (uint32_t)kMaxStage;
+    if (ok) p.P = P;
+  }
+  if (!p.P) {
+    if (k <= (uint32_t)kMaxStage) { p.P = 1; p.s[0] = k; }
+    else if (k <= 24) { p.P = 2; p.s[0] = (k + 1) / 2; p.s[1] = k - p.s[0]; }
+    else { p.P = 3; p.s[0] = (k + 2) / 3; p.s[1] = (k - p.s[0] + 1) / 2; p.s[2] = k - p.s[0] - p.s[1]; }
+  }
+  uint32_t tile_log = 11;  // 2048 elements = 64 KiB per CTA by default
+  const char* te = getenv("B200ZK_NTT_TILE_LOG");
+  if (te && *te) tile_log = (uint32_t)strtoul(te, nullptr, 10);
+  if (tile_log > (uint32_t)kMaxStage) tile_log = kMaxStage;
+  for (int i = 0; i < p.P; ++i) {
+    uint32_t tl = tile_log < p.s[i] ? p.s[i] : tile_log;
+    p.t[i] = tl - p.s[i];
+    uint32_t jbits = k - p.s[i];  // number of j values = 2^(k-s)
+    if (p.t[i] > jbits) p.t[i] = jbits;
+  }
+  return p;
+}
+
+static int launch_pass(b200zk_ctx* ctx, const PassArgs& a, cudaStream_t st) {
+  const uint32_t items = 1u << (a.s + a.t);
+  const size_t smem = (size_t)items * 32;
+  const unsigned grid = 1u << (a.log_n - a.s - a.t);
+  if (items >= 4096) {
+    static bool attr512 = false;
+    if (!attr512) { B2_CUDA(ctx, cudaFuncSetAttribute(ntt_pass<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 17)); attr512 = true; }
+    B2_LAUNCH(ctx, ntt_pass<512>, grid, 512, smem, st, a);
+  } else {
+    static bool attr256 = false;
+    if (!attr256) { B2_CUDA(ctx, cudaFuncSetAttribute(ntt_pass<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16)); attr256 = true; }
+    B2_LAUNCH(ctx, ntt_pass<256>, grid, 256, smem, st, a);
+  }
+  return B200ZK_OK;
+}
+
+int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st) {
+  if (log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: log_n > 28 (two-adicity of Fr)");
+  const size_t n = (size_t)1 << log_n;
+  const bool inverse = flags & B200ZK_NTT_INVERSE, coset = flags & B200ZK_NTT_COSET;
+  const bool canonical = flags & (B200ZK_NTT_CANONICAL | B200ZK_NTT_BE), be = flags & B200ZK_NTT_BE;
+  const unsigned egrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
+  if (canonical) B2_LAUNCH(ctx, fr_convert, egrid, 256, 0, st, d_data, n, 1, be ? 1 : 0);
+
+  // coset tables (per call: the generator is an argument)
+  void *c_lo = nullptr, *c_hi = nullptr;
+  const uint32_t lb = log_n < (uint32_t)kLoBits ? log_n : (uint32_t)kLoBits;
+  const uint32_t n_lo = 1u << lb, n_hi = log_n > (uint32_t)kLoBits ? 1u << (log_n - kLoBits) : 1u;
+  if (coset) {
+    B2_TRY(ensure(ctx, ctx->ws_misc, (size_t)(n_lo + n_hi) * 32 + 64));
+    uint32_t h[8] = {5, 0, 0, 0, 0, 0, 0, 0};
+    if (coset_gen) {
+      if (be) for (int i = 0; i < 8; ++i) h[i] = ((uint32_t)coset_gen[31 - 4 * i]) | ((uint32_t)coset_gen[30 - 4 * i] << 8) | ((uint32_t)coset_gen[29 - 4 * i] << 16) | ((uint32_t)coset_gen[28 - 4 * i] << 24);
+      else memcpy(h, coset_gen, 32);
+    }
+    uint8_t* base = (uint8_t*)ctx->ws_misc.p;
+    B2_CUDA(ctx, cudaMemcpyAsync(base, h, 32, cudaMemcpyHostToDevice, st));
+    B2_CUDA(ctx, cudaStreamSynchronize(st));  // h is a stack buffer
+    c_lo = base + 64; c_hi = base + 64 + (size_t)n_lo * 32;
+    B2_LAUNCH(ctx, ntt_build_pow_tables, (n_lo + n_hi + 127) / 128, 128, 0, st, (const uint32_t*)base, inverse ? 1 : 0, inverse ? 1 : 0, log_n, c_lo, n_lo, c_hi, n_hi);
+    if (!inverse) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, log_n > (uint32_t)kLoBits ? 1 : 0);
+  }
+
+  if (log_n > 0) {
+    NttTables tb;
+    B2_TRY(get_tables(ctx, log_n, inverse, st, &tb));
+    Plan pl = make_ntt_plan(log_n);
+    if (pl.P > 1) B2_TRY(ensure(ctx, ctx->ws_ntt, n * 32));
+    void* bufs[2] = {d_data, ctx->ws_ntt.p};
+    uint32_t log_ns = 0;
+    int cur = 0;
+    for (int p = 0; p < pl.P; ++p) {
+      PassArgs a;
+      a.in = bufs[cur];
+      a.out = pl.P == 1 ? d_data : bufs[cur ^ 1];
+      a.log_n = log_n; a.s = pl.s[p]; a.t = pl.t[p]; a.log_ns = log_ns;
+      a.scale_out = (inverse && !coset && p == pl.P - 1) ? 1 : 0;
+      a.tb = tb;
+      B2_TRY(launch_pass(ctx, a, st));
+      log_ns += pl.s[p];
+      if (pl.P > 1) cur ^= 1;
+    }
+    if (pl.P > 1 && cur == 1) B2_CUDA(ctx, cudaMemcpyAsync(d_data, ctx->ws_ntt.p, n * 32, cudaMemcpyDeviceToDevice, st));
+  }
+  if (coset && inverse) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, log_n > (uint32_t)kLoBits ? 1 : 0);
+  if (canonical) B2_LAUNCH(ctx, fr_convert, egrid, 256, 0, st, d_data, n, 0, be ? 1 : 0);
+  return B200ZK_OK;
+}
+
+}  // namespace b200zk

@@ -1,0 +1,171 @@
+/* b200zk.h -- frozen C ABI of libb200zk.so, the B200 (sm_100a) BN254 MSM + Fr NTT backend.
+ *
+ * This is the drop-in boundary for ethrex's L2 prover hot path: the entry points a
+ * `crates/prover/src/backend/b200.rs` ProverBackend implementation binds through `unsafe extern "C"`
+ * (the binding a maintainer adds is shown in INTEGRATION.md and rust/b200zk-sys/src/lib.rs).
+ *
+ * Conventions follow the in-tree C-ABI precedent
+ *   /root/reference/crates/guest-program/src/crypto/zisk.rs:5-64   (declarations)
+ *   /root/reference/crates/guest-program/src/crypto/zisk.rs:144-172 (status codes 0/1/2/3)
+ * i.e. caller-owned buffers, plain pointers and sizes, small integer status, nothing allocated across the
+ * boundary except opaque handles.  No torch / CUDA types appear in any signature: device pointers and
+ * streams travel as `void*` (a `cudaStream_t` is a pointer).
+ *
+ * Byte formats
+ *   "BE"      32-byte big-endian canonical field elements, the EIP-196/197 wire format of
+ *             /root/reference/crates/common/crypto/provider.rs:201-330: G1 = x|y (64 B), (0,0) = identity;
+ *             G2 = x_im|x_re|y_im|y_re (128 B); coordinates >= p are rejected like
+ *             /root/reference/crates/vm/levm/src/precompiles.rs:801-820.
+ *   "native"  little-endian limbs (bytes of 4 x u64 == 8 x u32 on a little-endian host).  Field elements of
+ *             points and NTT data are in Montgomery form with R = 2^256 -- the in-memory form of ark-ff
+ *             0.5.0 Fp256<MontBackend> that the SNARK wrap behind ProofFormat::Groth16
+ *             (/root/reference/crates/prover/src/backend/sp1.rs:97-134, risc0.rs:24-29) holds its proving
+ *             key in.  G1 affine = x|y (64 B), G2 affine = x.c0|x.c1|y.c0|y.c1 (128 B), (0,..,0) = identity.
+ *             Scalars are canonical (non-Montgomery) 256-bit integers (ark `into_bigint()`), reduced mod r by
+ *             the library, unless B200ZK_SCALARS_MONT is set.
+ *
+ * Semantics
+ *   MSM  = ark_ec::VariableBaseMSM::msm (ark-ec 0.5.0, /root/reference/Cargo.lock:978): sum_i s_i * P_i,
+ *          returned as the affine point -- the value is algorithm independent, so "bit exact" means equal
+ *          (x, y).
+ *   NTT  = ark_poly::Radix2EvaluationDomain (ark-poly 0.5.0, /root/reference/Cargo.lock:1140), equal to
+ *          gnark-crypto's bn254 fr/fft: natural order in and out, out[k] = sum_j a[j] w^{jk},
+ *          w = 5^((r-1)/2^28)^(2^(28-log_n)); inverse uses w^-1 and scales by n^-1; coset pre-multiplies a[j]
+ *          by h^j (forward) / post-multiplies by h^-j (inverse), h = 5 unless given.
+ *
+ * There is NO CPU fallback anywhere behind this interface: without a CUDA device b200zk_init fails with
+ * B200ZK_ERR_NO_DEVICE and every other call fails with B200ZK_ERR_INVALID_ARG on the NULL context.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ZK_ABI_VERSION 1
+
+typedef struct b200zk_ctx b200zk_ctx;
+
+/* status codes: 0..3 are the ZisK table (zisk.rs:144-172); the rest are this library's own failures */
+enum {
+  B200ZK_OK = 0,
+  B200ZK_OK_INFINITY = 1,       /* success, result is the identity */
+  B200ZK_ERR_NOT_IN_FIELD = 2,  /* a BE coordinate is >= p */
+  B200ZK_ERR_NOT_ON_CURVE = 3,  /* a BE point does not satisfy the curve equation */
+  B200ZK_ERR_INVALID_ARG = 4,
+  B200ZK_ERR_CUDA = 5,
+  B200ZK_ERR_NO_DEVICE = 6,
+  B200ZK_ERR_OOM = 7,
+  B200ZK_ERR_UNSUPPORTED = 8
+};
+
+/* flags */
+enum {
+  B200ZK_POINTS_BE = 1u << 0,       /* points are EIP-196/197 big-endian bytes (validated); default native */
+  B200ZK_SCALARS_BE = 1u << 1,      /* scalars are 32-byte big-endian; default little-endian limbs */
+  B200ZK_SCALARS_MONT = 1u << 2,    /* scalars are Montgomery-form limbs (ark Fr in-memory form) */
+  B200ZK_OUT_NATIVE = 1u << 3,      /* MSM result as native affine limbs instead of BE bytes */
+  B200ZK_NTT_INVERSE = 1u << 4,
+  B200ZK_NTT_COSET = 1u << 5,
+  B200ZK_NTT_CANONICAL = 1u << 6,   /* NTT data are canonical little-endian limbs (converted on device) */
+  B200ZK_NTT_BE = 1u << 7           /* NTT data are 32-byte big-endian canonical values */
+};
+
+/* ---- lifecycle (ProverBackend::new / process-global OnceLock, cf. sp1.rs:30,93-95) ------------------- */
+int b200zk_abi_version(void);
+int b200zk_device_count(void);
+int b200zk_init(int device, b200zk_ctx** out);
+void b200zk_destroy(b200zk_ctx* ctx);
+const char* b200zk_strerror(int status);
+const char* b200zk_last_error(const b200zk_ctx* ctx); /* detail of the last failure on this context */
+/* number of kernels this context has launched since init (bench.py's gpu_launches claim) */
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx);
+int b200zk_synchronize(b200zk_ctx* ctx);
+
+/* ---- host-buffer entry points: what the Rust backend calls.  Copies are part of the call. -------------- */
+/* replaces ark_ec::VariableBaseMSM::msm for G1Affine / G2Affine */
+int b200zk_g1_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags,
+                  uint8_t out[64]);
+int b200zk_g2_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags,
+                  uint8_t out[128]);
+/* replaces ark_poly::Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place (row a8);
+ * n = 2^log_n elements of 32 bytes, transformed in place in the caller's buffer. coset_gen: 32-byte
+ * canonical value in the same endianness family as the data (LE limbs, or BE with B200ZK_NTT_BE); NULL = 5 */
+int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen);
+
+/* ---- resident bases: the proving key (SRS) lives in HBM across proofs ---------------------------------- */
+int b200zk_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle);
+int b200zk_g2_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle);
+int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle);
+/* MSM of the first n resident bases against host scalars */
+int b200zk_g1_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
+                           uint8_t out[64]);
+int b200zk_g2_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
+                           uint8_t out[128]);
+
+/* ---- device-pointer entry points: inputs already in HBM (native formats only) ------------------------- */
+/* `stream`: a cudaStream_t passed as void*; NULL = the context's own stream.  The *_device calls enqueue
+ * every kernel on that stream, then copy the 64/128-byte result to `out` and wait for it. */
+int b200zk_g1_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
+                         uint32_t flags, void* stream, uint8_t out[64]);
+int b200zk_g2_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
+                         uint32_t flags, void* stream, uint8_t out[128]);
+/* fully asynchronous forms: the encoded result (BE or native per flags) is written to device memory */
+int b200zk_g1_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
+                               uint32_t flags, void* stream, void* d_out64);
+int b200zk_g2_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
+                               uint32_t flags, void* stream, void* d_out128);
+int b200zk_fr_ntt_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags,
+                         const uint8_t* coset_gen, void* stream);
+
+/* ---- multi-GPU: one process per GPU, point-split MSM ------------------------------------ */
+/* Each rank reduces its shard to ONE partial sum in extended-Jacobian XYZZ form (G1: 128 B, G2: 256 B,
+ * native Montgomery limbs) left in device memory; the host side all-gathers the partials over NCCL and
+ * every rank folds them with b200zk_g{1,2}_fold_partials_device -- NCCL has no elliptic-curve reduce op, so
+ * this pair is the "allreduce of partial sums". */
+int b200zk_g1_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
+                                 uint32_t flags, void* stream, void* d_partial128);
+int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
+                                 uint32_t flags, void* stream, void* d_partial256);
+int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags,
+                                   void* stream, uint8_t out[64]);
+int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags,
+                                   void* stream, uint8_t out[128]);
+
+/* ---- device utilities (format conversion, synthetic workloads; used by tests and bench.py) ------------- */
+/* canonical LE limbs <-> Montgomery limbs, in place in device memory; which = 0 for Fq, 1 for Fr */
+int b200zk_field_to_mont_device(b200zk_ctx* ctx, void* d_data, size_t n, int which, void* stream);
+int b200zk_field_from_mont_device(b200zk_ctx* ctx, void* d_data, size_t n, int which, void* stream);
+/* out[i] = a[i] * b[i] (Montgomery product), the field core exposed for parity tests and microbenchmarks;
+ * `repeat` > 1 chains out = out * b that many times (throughput measurement) */
+int b200zk_field_mul_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, void* d_out, size_t n,
+                            int which, uint32_t repeat, void* stream);
+/* counter-based splitmix64 scalars: element i = reduce_mod_r(4 outputs of state seed + 4*(start+i)*golden)
+ * (SURVEY.md 8d); canonical limbs, or Montgomery with B200ZK_SCALARS_MONT */
+int b200zk_fr_random_device(b200zk_ctx* ctx, void* d_out, size_t n, uint64_t seed, uint64_t start,
+                            uint32_t flags, void* stream);
+/* synthetic base chain P_i = (k + i*d) * G for i in [start, start+n) (native affine);
+ * k, d: canonical LE 32-byte scalars */
+int b200zk_g1_chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, const uint8_t k[32],
+                           const uint8_t d[32], void* stream);
+int b200zk_g2_chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, const uint8_t k[32],
+                           const uint8_t d[32], void* stream);
+/* on-curve check of n native affine points; *bad_index = first offending index or n */
+int b200zk_g1_check_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, size_t* bad_index);
+int b200zk_g2_check_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, size_t* bad_index);
+
+/* tuning knobs (0 = automatic): window bits for the next MSM calls on this context */
+int b200zk_set_msm_window(b200zk_ctx* ctx, uint32_t c);
+/* per-phase device time of the last *_device MSM call, in milliseconds:
+ * [0] digit histogram, [1] scan, [2] scatter, [3] bucket accumulation, [4] bucket reduction, [5] final */
+int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]);
+int b200zk_set_profiling(b200zk_ctx* ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

@@ -1,0 +1,135 @@
+//! Safe wrapper over the raw C ABI (`b200zk-sys`).  One process-global context, like the reference's
+//! `static PROVER_SETUP: OnceLock<ProverSetup>` (`crates/prover/src/backend/sp1.rs:30,93-95`).
+//! Obeys the prover crate's lint policy (`crates/prover/Cargo.toml:72-80`): no unwrap / expect / panic /
+//! indexing / `as`.
+use std::ffi::CStr;
+use std::ptr::NonNull;
+use std::sync::{Mutex, OnceLock};
+
+use b200zk_sys as sys;
+use ethrex_prover::backend::BackendError;
+
+/// Owned `b200zk_ctx*`.  The library serialises work on its own stream; the `Mutex` in [`global`] makes the
+/// handle usable from the prover actor's blocking thread (`crates/prover/src/prover.rs:240-251`) or any other.
+pub struct B200zk {
+    ctx: NonNull<sys::b200zk_ctx>,
+}
+
+// SAFETY: the context owns only device resources and is never aliased outside the Mutex in `global()`.
+unsafe impl Send for B200zk {}
+
+static GLOBAL: OnceLock<Result<Mutex<B200zk>, String>> = OnceLock::new();
+
+/// Lazily initialised process-global context on the device selected by `CUDA_VISIBLE_DEVICES`.
+pub fn global() -> Result<&'static Mutex<B200zk>, BackendError> {
+    GLOBAL
+        .get_or_init(|| B200zk::new(0).map(Mutex::new).map_err(|e| e.to_string()))
+        .as_ref()
+        .map_err(BackendError::proving)
+}
+
+fn status_message(ctx: Option<&B200zk>, status: i32) -> String {
+    // SAFETY: both functions return NUL-terminated strings owned by the library / the context.
+    let base = unsafe { CStr::from_ptr(sys::b200zk_strerror(status)) }.to_string_lossy().into_owned();
+    match ctx {
+        Some(c) => {
+            let detail = unsafe { CStr::from_ptr(sys::b200zk_last_error(c.ctx.as_ptr())) }.to_string_lossy().into_owned();
+            format!("b200zk status {status}: {base} ({detail})")
+        }
+        None => format!("b200zk status {status}: {base}"),
+    }
+}
+
+/// C status -> `BackendError` (the table INTEGRATION.md documents): malformed input is a serialization
+/// error, everything the device reports is a proving error.
+fn check(ctx: &B200zk, status: i32) -> Result<bool, BackendError> {
+    match status {
+        sys::B200ZK_OK => Ok(false),
+        sys::B200ZK_OK_INFINITY => Ok(true),
+        sys::B200ZK_ERR_NOT_IN_FIELD | sys::B200ZK_ERR_NOT_ON_CURVE | sys::B200ZK_ERR_INVALID_ARG => {
+            Err(BackendError::serialization(status_message(Some(ctx), status)))
+        }
+        sys::B200ZK_ERR_UNSUPPORTED => Err(BackendError::not_implemented(status_message(Some(ctx), status))),
+        other => Err(BackendError::proving(status_message(Some(ctx), other))),
+    }
+}
+
+impl B200zk {
+    pub fn new(device: i32) -> Result<Self, BackendError> {
+        let mut raw: *mut sys::b200zk_ctx = std::ptr::null_mut();
+        // SAFETY: `raw` is a valid out-pointer.
+        let status = unsafe { sys::b200zk_init(device, &mut raw) };
+        match NonNull::new(raw) {
+            Some(ctx) if status == sys::B200ZK_OK => Ok(Self { ctx }),
+            _ => Err(BackendError::proving(status_message(None, status))),
+        }
+    }
+
+    /// sum_i scalars[i] * bases[i] over BN254 G1.  `points`: n x 64 bytes, `scalars`: n x 32 bytes, formats per
+    /// `flags` (see include/b200zk.h).  Returns the 64-byte EIP-196 encoding.
+    pub fn g1_msm(&mut self, points: &[u8], scalars: &[u8], flags: u32) -> Result<[u8; 64], BackendError> {
+        let n = scalars.len() / 32;
+        if points.len() / 64 < n {
+            return Err(BackendError::serialization("g1_msm: fewer points than scalars"));
+        }
+        let mut out = [0u8; 64];
+        // SAFETY: lengths checked above; buffers outlive the (synchronous) call.
+        let status = unsafe {
+            sys::b200zk_g1_msm(self.ctx.as_ptr(), points.as_ptr().cast(), scalars.as_ptr().cast(), n, flags, out.as_mut_ptr())
+        };
+        check(self, status)?;
+        Ok(out)
+    }
+
+    pub fn g2_msm(&mut self, points: &[u8], scalars: &[u8], flags: u32) -> Result<[u8; 128], BackendError> {
+        let n = scalars.len() / 32;
+        if points.len() / 128 < n {
+            return Err(BackendError::serialization("g2_msm: fewer points than scalars"));
+        }
+        let mut out = [0u8; 128];
+        // SAFETY: as above.
+        let status = unsafe {
+            sys::b200zk_g2_msm(self.ctx.as_ptr(), points.as_ptr().cast(), scalars.as_ptr().cast(), n, flags, out.as_mut_ptr())
+        };
+        check(self, status)?;
+        Ok(out)
+    }
+
+    /// In-place NTT of `data` (2^log_n x 32 bytes).
+    pub fn fr_ntt(&mut self, data: &mut [u8], log_n: u32, flags: u32, coset_gen: Option<&[u8; 32]>) -> Result<(), BackendError> {
+        let want = 32usize.checked_shl(log_n).ok_or_else(|| BackendError::serialization("fr_ntt: log_n too large"))?;
+        if data.len() != want {
+            return Err(BackendError::serialization("fr_ntt: buffer length is not 32 * 2^log_n"));
+        }
+        let cg = coset_gen.map_or(std::ptr::null(), |g| g.as_ptr());
+        // SAFETY: length checked above.
+        let status = unsafe { sys::b200zk_fr_ntt(self.ctx.as_ptr(), data.as_mut_ptr().cast(), log_n, flags, cg) };
+        check(self, status).map(|_| ())
+    }
+
+    /// Uploads a proving-key column once; later proofs only ship scalars.
+    pub fn g1_bases_upload(&mut self, points: &[u8], flags: u32) -> Result<u64, BackendError> {
+        let mut handle = 0u64;
+        // SAFETY: slice is valid for points.len() bytes.
+        let status = unsafe { sys::b200zk_g1_bases_upload(self.ctx.as_ptr(), points.as_ptr().cast(), points.len() / 64, flags, &mut handle) };
+        check(self, status)?;
+        Ok(handle)
+    }
+
+    pub fn g1_msm_resident(&mut self, handle: u64, scalars: &[u8], flags: u32) -> Result<[u8; 64], BackendError> {
+        let mut out = [0u8; 64];
+        // SAFETY: slice valid; n derived from its length.
+        let status = unsafe {
+            sys::b200zk_g1_msm_resident(self.ctx.as_ptr(), handle, scalars.as_ptr().cast(), scalars.len() / 32, flags, out.as_mut_ptr())
+        };
+        check(self, status)?;
+        Ok(out)
+    }
+}
+
+impl Drop for B200zk {
+    fn drop(&mut self) {
+        // SAFETY: ctx came from b200zk_init and is dropped exactly once.
+        unsafe { sys::b200zk_destroy(self.ctx.as_ptr()) }
+    }
+}

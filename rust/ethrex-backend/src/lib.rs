@@ -1,0 +1,4 @@
+//! B200 prover backend for ethrex: safe wrapper over `b200zk-sys` plus the `ProverBackend` implementation.
+pub mod b200;
+pub mod ffi;
+pub use b200::B200Backend;

@@ -1,0 +1,372 @@
+"""GPU parity tests: libb200zk.so (through the C ABI) against the CPU oracle, bit exact.
+
+Mirrors the shape of the reference's precompile KAT tests
+(/root/reference/test/tests/levm/precompile_tests.rs:6-151: feed bytes, compare bytes, check the error
+variant) for the operations of SURVEY.md section 8a rows a6-a8.
+"""
+import numpy as np
+import pytest
+
+import cpu_oracle as orc
+import pyref
+from helpers import (chain_kd, dev_empty, expected_chain_msm_g1, expected_chain_msm_g2, scalars_special, to_dev,
+                     to_host)
+
+pytestmark = pytest.mark.gpu
+
+import ethrex_b200 as eb  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------ field core
+@pytest.mark.parametrize("which,field", [(0, "fq"), (1, "fr")])
+def test_field_mul_matches_oracle(ctx, which, field):
+    n = 4096
+    mod = pyref.P if which == 0 else pyref.R
+    rng = np.random.default_rng(1234 + which)
+    vals_a = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(n)]
+    vals_b = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(n)]
+    # edge values: 0, 1, p-1, R mod p ...
+    edge = [0, 1, mod - 1, mod - 2, (1 << 256) % mod, 2, (1 << 253) % mod]
+    for i, e in enumerate(edge):
+        vals_a[i] = e
+        vals_b[-1 - i] = e
+        vals_b[i] = edge[(i * 3) % len(edge)]
+    a, b = orc.ints_to_array(vals_a), orc.ints_to_array(vals_b)
+    da, db, do = to_dev(a), to_dev(b), dev_empty(4 * n)
+    ctx.field_mul_device(da, db, do, n, which)
+    got = to_host(do).reshape(n, 4)
+    assert (got == orc.field_mul(field, a, b)).all()
+    # chained products (the throughput path) == repeated oracle products
+    ctx.field_mul_device(da, db, do, n, which, repeat=5)
+    exp = a
+    for _ in range(5):
+        exp = orc.field_mul(field, exp, b)
+    assert (to_host(do).reshape(n, 4) == exp).all()
+
+
+def test_mont_roundtrip_and_random(ctx):
+    n = 5000
+    d = dev_empty(4 * n)
+    ctx.fr_random_device(d, n, pyref.SEED_SCALARS, 0)
+    host = to_host(d).reshape(n, 4)
+    assert (host == orc.rand_fr(pyref.SEED_SCALARS, 0, n)).all()
+    ctx.field_to_mont_device(d, n, 1)
+    assert (to_host(d).reshape(n, 4) == orc.fr_to_mont(host)).all()
+    ctx.field_from_mont_device(d, n, 1)
+    assert (to_host(d).reshape(n, 4) == host).all()
+    ctx.fr_random_device(d, n, pyref.SEED_NTT, 77, eb.SCALARS_MONT)
+    assert (to_host(d).reshape(n, 4) == orc.fr_to_mont(orc.rand_fr(pyref.SEED_NTT, 77, n))).all()
+
+
+# ------------------------------------------------------------------------------------------ synthetic bases
+def test_chain_generators_match_oracle(ctx):
+    k, d = chain_kd()
+    n = 300
+    g1 = dev_empty(8 * n)
+    ctx.g1_chain_device(g1, 5, n, k, d)
+    assert (to_host(g1).reshape(n, 8) == orc.g1_chain(n + 5, k, d)[5:]).all()
+    assert ctx.g1_check_device(g1, n) == n
+    g2 = dev_empty(16 * n)
+    ctx.g2_chain_device(g2, 0, n, k, d)
+    assert (to_host(g2).reshape(n, 16) == orc.g2_chain(n, k, d)).all()
+    assert ctx.g2_check_device(g2, n) == n
+    # corrupt one point: the checker must name it
+    h = to_host(g1).copy().reshape(n, 8)
+    h[123, 0] ^= 1
+    assert ctx.g1_check_device(to_dev(h), n) == 123
+
+
+# ------------------------------------------------------------------------------------------ NTT
+def _ntt_case(ctx, log_n, flags, coset_gen=None, seed=pyref.SEED_NTT):
+    n = 1 << log_n
+    a = orc.fr_to_mont(orc.rand_fr(seed, 0, n))
+    d = to_dev(a)
+    oflags = (orc.NTT_INVERSE if flags & eb.NTT_INVERSE else 0) | (orc.NTT_COSET if flags & eb.NTT_COSET else 0)
+    ctx.fr_ntt_device(d, log_n, flags, None if coset_gen is None else coset_gen.to_bytes(32, "little"))
+    exp = orc.fr_ntt(a, log_n, oflags, coset_gen=coset_gen)
+    got = to_host(d).reshape(n, 4)
+    assert (got == exp).all(), f"log_n={log_n} flags={flags}"
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 15)))
+def test_ntt_small_all_modes(ctx, log_n):
+    for flags in (0, eb.NTT_INVERSE, eb.NTT_COSET, eb.NTT_INVERSE | eb.NTT_COSET):
+        _ntt_case(ctx, log_n, flags)
+    _ntt_case(ctx, log_n, eb.NTT_COSET, coset_gen=7)
+    _ntt_case(ctx, log_n, eb.NTT_COSET | eb.NTT_INVERSE, coset_gen=pyref.R - 3)
+
+
+@pytest.mark.parametrize("log_n", [16, 17, 20, 22])
+def test_ntt_medium_vs_oracle(ctx, log_n):
+    _ntt_case(ctx, log_n, 0)
+    _ntt_case(ctx, log_n, eb.NTT_INVERSE)
+
+
+def test_ntt_golden_2_12(ctx):
+    """config #1: 2^12 forward against the pure-Python fixture (tests/golden/ntt_2_12.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ntt_2_12.npz"))
+    a = g["input_canonical"]
+    d = to_dev(a)
+    ctx.fr_ntt_device(d, 12, eb.NTT_CANONICAL)
+    assert (to_host(d).reshape(-1, 4) == g["forward_canonical"]).all()
+    ctx.fr_ntt_device(d, 12, eb.NTT_CANONICAL | eb.NTT_INVERSE)
+    assert (to_host(d).reshape(-1, 4) == a).all()
+
+
+def test_ntt_special_inputs(ctx):
+    log_n, n = 10, 1024
+    one_m = orc.fr_to_mont(orc.ints_to_array([1]))[0]
+    # delta at 0 -> all ones ; all ones -> n * delta
+    delta = np.zeros((n, 4), dtype=np.uint64)
+    delta[0] = one_m
+    d = to_dev(delta)
+    ctx.fr_ntt_device(d, log_n, 0)
+    assert (to_host(d).reshape(n, 4) == np.tile(one_m, (n, 1))).all()
+    ctx.fr_ntt_device(d, log_n, 0)
+    got = orc.array_to_ints(orc.fr_from_mont(to_host(d).reshape(n, 4)))
+    assert got[0] == n and all(v == 0 for v in got[1:])
+    # a[j] = j (canonical in/out path, big-endian flavour too)
+    ramp = orc.ints_to_array(list(range(n)))
+    d = to_dev(ramp)
+    ctx.fr_ntt_device(d, log_n, eb.NTT_CANONICAL)
+    assert orc.array_to_ints(to_host(d)) == pyref.ntt_fast(list(range(n)))
+    be = b"".join(pyref.fr_to_be(v) for v in range(n))
+    dbe = to_dev(np.frombuffer(be, dtype=np.uint64))
+    ctx.fr_ntt_device(dbe, log_n, eb.NTT_BE)
+    exp_be = b"".join(pyref.fr_to_be(v) for v in pyref.ntt_fast(list(range(n))))
+    assert to_host(dbe).tobytes() == exp_be
+
+
+def test_ntt_host_entry_point(ctx):
+    log_n, n = 13, 1 << 13
+    a = orc.fr_to_mont(orc.rand_fr(99, 0, n))
+    buf = a.copy()
+    ctx.fr_ntt(buf, log_n, 0)
+    assert (buf == orc.fr_ntt(a, log_n)).all()
+    ctx.fr_ntt(buf, log_n, eb.NTT_INVERSE)
+    assert (buf == a).all()
+
+
+def test_ntt_2_24_roundtrip_and_spot_check(ctx):
+    """config #3 at full size: iNTT(NTT(a)) == a, linearity probe, and direct evaluation of a few outputs."""
+    import torch
+    log_n, n = 24, 1 << 24
+    d = dev_empty(4 * n)
+    ctx.fr_random_device(d, n, pyref.SEED_NTT, 0, eb.SCALARS_MONT)
+    orig = d.clone()
+    ctx.fr_ntt_device(d, log_n, 0)
+    fwd = d.clone()
+    ctx.fr_ntt_device(d, log_n, eb.NTT_INVERSE)
+    assert torch.equal(d, orig)
+    # full compare against the CPU oracle's transform
+    exp = orc.fr_ntt(to_host(orig).reshape(n, 4), log_n)
+    assert (to_host(fwd).reshape(n, 4) == exp).all()
+
+
+# ------------------------------------------------------------------------------------------ MSM
+def _msm_g1_vs_oracle(ctx, n, scalars, method=0):
+    k, d = chain_kd()
+    pts = orc.g1_chain(max(n, 1), k, d)[:n]
+    got = ctx.g1_msm_device(to_dev(pts) if n else dev_empty(8), to_dev(scalars) if n else dev_empty(4), n)
+    assert got == orc.g1_msm(pts, scalars, method), f"n={n}"
+    return got
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 100, 1000, 4096])
+def test_g1_msm_small_vs_oracle(ctx, n):
+    _msm_g1_vs_oracle(ctx, n, scalars_special(n) if n else np.zeros((0, 4), dtype=np.uint64))
+
+
+def test_g1_msm_kats_from_reference(ctx):
+    """n=1 MSMs reproduce the reference's own scalar-multiplication KATs:
+    7*(1,2) (test/tests/l2/integration_tests.rs:572) and 2*(1,2)."""
+    g = orc.g1_be_to_native(pyref.g1_to_be(pyref.G1_GEN))
+    for s, exp in ((7, "17072b2ed3bb8d759a5325f477629386cb6fc6ecb801bd76983a6b86abffe078168ada6cd130dd52017bb54bfa19377aadfe3bf05d18f41b77809f7f60d4af9e"),
+                   (2, "030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd315ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4")):
+        got = ctx.g1_msm_device(to_dev(g), to_dev(orc.ints_to_array([s])), 1)
+        assert got.hex() == exp
+    # r*G = identity -> (0,0) and status OK_INFINITY is folded into the bytes
+    assert ctx.g1_msm_device(to_dev(g), to_dev(orc.ints_to_array([pyref.R])), 1) == bytes(64)
+
+
+def test_g1_msm_edge_distributions(ctx):
+    k, d = chain_kd()
+    n = 2048
+    pts = orc.g1_chain(n, k, d)
+    dp = to_dev(pts)
+    cases = {
+        "all_zero": [0] * n,
+        "all_one": [1] * n,
+        "all_r_minus_1": [pyref.R - 1] * n,
+        "small": [(i * 2654435761) & 0xFFFF for i in range(n)],
+        "half_zero": [0 if i & 1 else pyref.rand_fr(5, i) for i in range(n)],
+        "unreduced": [pyref.R + 5 + i for i in range(n)],          # >= r: reduced mod r by the library
+        "max_u256": [(1 << 256) - 1 - i for i in range(n)],
+    }
+    for name, vals in cases.items():
+        s = orc.ints_to_array(vals)
+        assert ctx.g1_msm_device(dp, to_dev(s), n) == orc.g1_msm(pts, s), name
+    # repeated points, P and -P pairs, identity points among the bases
+    pts2 = pts.copy()
+    pts2[1] = pts2[0]
+    pts2[3] = pts2[2]
+    neg = orc.g1_be_to_native(pyref.g1_to_be(pyref.pt_neg(pyref._Fq, pyref.g1_from_be(orc.g1_native_to_be(pts[4:5])))))
+    pts2[5] = neg[0]
+    pts2[7] = 0
+    s = orc.rand_fr(11, 0, n)
+    s[1] = s[0]
+    s[5] = s[4]
+    s[3] = orc.int_to_limbs((pyref.R - orc.limbs_to_int(s[2])) % pyref.R)
+    assert ctx.g1_msm_device(to_dev(pts2), to_dev(s), n) == orc.g1_msm(pts2, s)
+
+
+def test_g1_msm_window_sweep(ctx):
+    k, d = chain_kd()
+    n = 3000
+    pts, s = orc.g1_chain(n, k, d), scalars_special(n)
+    exp = orc.g1_msm(pts, s)
+    dp, ds = to_dev(pts), to_dev(s)
+    try:
+        for c in (2, 3, 5, 8, 11, 13, 16):
+            ctx.set_msm_window(c)
+            assert ctx.g1_msm_device(dp, ds, n) == exp, f"c={c}"
+    finally:
+        ctx.set_msm_window(0)
+
+
+def test_g1_msm_scalar_formats(ctx):
+    k, d = chain_kd()
+    n = 777
+    pts, s = orc.g1_chain(n, k, d), scalars_special(n)
+    exp = orc.g1_msm(pts, s)
+    dp = to_dev(pts)
+    assert ctx.g1_msm_device(dp, to_dev(orc.fr_to_mont(s)), n, eb.SCALARS_MONT) == exp
+    be = b"".join(pyref.fr_to_be(v) for v in orc.array_to_ints(s))
+    assert ctx.g1_msm_device(dp, to_dev(np.frombuffer(be, dtype=np.uint64)), n, eb.SCALARS_BE) == exp
+    native = ctx.g1_msm_device(dp, to_dev(s), n, eb.OUT_NATIVE)
+    assert orc.g1_native_to_be(np.frombuffer(native, dtype=np.uint64)) == exp
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_g1_msm_large_closed_form(ctx, log_n):
+    """config #2 (2^20): synthetic chain bases make the exact result a single scalar multiplication."""
+    n = 1 << log_n
+    k, d = chain_kd()
+    dp, ds = dev_empty(8 * n), dev_empty(4 * n)
+    ctx.g1_chain_device(dp, 0, n, k, d)
+    ctx.fr_random_device(ds, n, pyref.SEED_SCALARS, 0)
+    got = ctx.g1_msm_device(dp, ds, n)
+    s = to_host(ds).reshape(n, 4)
+    assert got == expected_chain_msm_g1(s, k, d)
+    if log_n == 16:
+        assert got == orc.g1_msm(to_host(dp).reshape(n, 8), s)
+
+
+def test_g1_msm_2_24_closed_form(ctx):
+    n = 1 << 24
+    k, d = chain_kd()
+    dp, ds = dev_empty(8 * n), dev_empty(4 * n)
+    ctx.g1_chain_device(dp, 0, n, k, d)
+    assert ctx.g1_check_device(dp, n) == n
+    ctx.fr_random_device(ds, n, pyref.SEED_SCALARS, 0)
+    got = ctx.g1_msm_device(dp, ds, n)
+    assert got == expected_chain_msm_g1(to_host(ds).reshape(n, 4), k, d)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 500, 4096])
+def test_g2_msm_small_vs_oracle(ctx, n):
+    k, d = chain_kd()
+    pts = orc.g2_chain(max(n, 1), k, d)[:n]
+    s = scalars_special(n) if n else np.zeros((0, 4), dtype=np.uint64)
+    got = ctx.g2_msm_device(to_dev(pts) if n else dev_empty(16), to_dev(s) if n else dev_empty(4), n)
+    assert got == orc.g2_msm(pts, s)
+
+
+def test_g2_msm_2_18_closed_form(ctx):
+    n = 1 << 18
+    k, d = chain_kd()
+    dp, ds = dev_empty(16 * n), dev_empty(4 * n)
+    ctx.g2_chain_device(dp, 0, n, k, d)
+    ctx.fr_random_device(ds, n, pyref.SEED_SCALARS, 0)
+    assert ctx.g2_msm_device(dp, ds, n) == expected_chain_msm_g2(to_host(ds).reshape(n, 4), k, d)
+
+
+# ------------------------------------------------------------------------------------------ host entry points, errors
+def test_host_msm_be_and_native(ctx):
+    k, d = chain_kd()
+    n = 600
+    pts, s = orc.g1_chain(n, k, d), scalars_special(n)
+    exp = orc.g1_msm(pts, s)
+    assert ctx.g1_msm(pts, s, n) == exp
+    be_pts = orc.g1_native_to_be(pts)
+    be_s = b"".join(pyref.fr_to_be(v) for v in orc.array_to_ints(s))
+    assert ctx.g1_msm(be_pts, be_s, n, eb.POINTS_BE | eb.SCALARS_BE) == exp
+    pts2 = orc.g2_chain(n, k, d)
+    exp2 = orc.g2_msm(pts2, s)
+    assert ctx.g2_msm(pts2, s, n) == exp2
+    assert ctx.g2_msm(orc.g2_native_to_be(pts2), be_s, n, eb.POINTS_BE | eb.SCALARS_BE) == exp2
+
+
+def test_host_msm_rejects_bad_points(ctx):
+    """error behaviour of provider.rs:217-219 / precompiles.rs:801-820: not on curve, coordinate >= p."""
+    g = pyref.g1_to_be(pyref.G1_GEN)
+    s = (5).to_bytes(32, "big")
+    bad_curve = (1).to_bytes(32, "big") + (3).to_bytes(32, "big")
+    with pytest.raises(eb.B200Error) as e:
+        ctx.g1_msm(g + bad_curve, s + s, 2, eb.POINTS_BE | eb.SCALARS_BE)
+    assert e.value.status == 3 and e.value.kind == "Serialization"
+    # the out-of-range x of precompile_tests.rs:143-151 (p+1, p+2)
+    oob = (pyref.P + 1).to_bytes(32, "big") + (pyref.P + 2).to_bytes(32, "big")
+    with pytest.raises(eb.B200Error) as e:
+        ctx.g1_msm(oob + g, s + s, 2, eb.POINTS_BE | eb.SCALARS_BE)
+    assert e.value.status == 2
+    # identity encodes as (0,0) and is accepted
+    assert ctx.g1_msm(bytes(64) + g, s + s, 2, eb.POINTS_BE | eb.SCALARS_BE) == pyref.g1_to_be(pyref.g1_mul(5, pyref.G1_GEN))
+
+
+def test_resident_bases(ctx):
+    k, d = chain_kd()
+    n = 5000
+    pts = orc.g1_chain(n, k, d)
+    h = ctx.g1_bases_upload(pts, n)
+    try:
+        for m in (n, 1234, 1):
+            s = orc.rand_fr(m, 0, m)
+            assert ctx.g1_msm_resident(h, s, m) == orc.g1_msm(pts[:m], s)
+        with pytest.raises(eb.B200Error):
+            ctx.g1_msm_resident(h, orc.rand_fr(1, 0, n + 1), n + 1)
+        with pytest.raises(eb.B200Error):
+            ctx.g2_msm_resident(h, orc.rand_fr(1, 0, 4), 4)
+    finally:
+        ctx.bases_free(h)
+    pts2 = orc.g2_chain(300, k, d)
+    h2 = ctx.g2_bases_upload(orc.g2_native_to_be(pts2), 300, eb.POINTS_BE)
+    s = orc.rand_fr(3, 0, 300)
+    assert ctx.g2_msm_resident(h2, s, 300) == orc.g2_msm(pts2, s)
+    ctx.bases_free(h2)
+
+
+def test_partials_fold_equals_whole(ctx):
+    """the multi-GPU combine on one device: MSM(shard0) + MSM(shard1) + ... == MSM(all)."""
+    import torch
+    k, d = chain_kd()
+    n, shards = 6000, 4
+    pts, s = orc.g1_chain(n, k, d), orc.rand_fr(21, 0, n)
+    parts = torch.zeros(shards * 16, dtype=torch.int64, device="cuda")
+    per = n // shards
+    for r in range(shards):
+        ctx.g1_msm_partial_device(to_dev(pts[r * per:(r + 1) * per]), to_dev(s[r * per:(r + 1) * per]), per, parts[r * 16:(r + 1) * 16])
+    assert ctx.g1_fold_partials_device(parts, shards) == orc.g1_msm(pts, s)
+    pts2 = orc.g2_chain(1000, k, d)
+    parts2 = torch.zeros(2 * 32, dtype=torch.int64, device="cuda")
+    ctx.g2_msm_partial_device(to_dev(pts2[:500]), to_dev(s[:500]), 500, parts2[:32])
+    ctx.g2_msm_partial_device(to_dev(pts2[500:]), to_dev(s[500:1000]), 500, parts2[32:])
+    assert ctx.g2_fold_partials_device(parts2, 2) == orc.g2_msm(pts2, s[:1000])
+
+
+def test_launch_counter_moves(ctx):
+    before = ctx.launch_count
+    d = dev_empty(4 * 16)
+    ctx.fr_random_device(d, 16, 1, 0)
+    assert ctx.launch_count == before + 1

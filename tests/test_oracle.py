@@ -1,0 +1,135 @@
+"""CPU tests: pin the C++ oracle against the pure-Python reference, the golden fixtures and the KATs the
+reference itself holds.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+import cpu_oracle as orc
+import pyref as o
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_constants_match_reference_sources():
+    # ALT_BN128_PRIME, /root/reference/crates/vm/levm/src/precompiles.rs:746-751 (little-endian u64 limbs)
+    limbs = [0x3c208c16d87cfd47, 0x97816a916871ca8d, 0xb85045b68181585d, 0x30644e72e131a029]
+    assert sum(v << (64 * i) for i, v in enumerate(limbs)) == o.P
+    assert (o.R - 1) % (1 << 28) == 0 and (o.R - 1) % (1 << 29) != 0
+    assert pow(o.ROOT_2_28, 1 << 28, o.R) == 1 and pow(o.ROOT_2_28, 1 << 27, o.R) == o.R - 1
+
+
+def test_reference_kats_scalar_mul():
+    g = o.g1_to_be(o.G1_GEN)
+    # 7*(1,2): /root/reference/test/tests/l2/integration_tests.rs:572
+    rc, out = orc.g1_mul_be(g, (7).to_bytes(32, "big"))
+    assert rc == 0 and out.hex() == ("17072b2ed3bb8d759a5325f477629386cb6fc6ecb801bd76983a6b86abffe078"
+                                     "168ada6cd130dd52017bb54bfa19377aadfe3bf05d18f41b77809f7f60d4af9e")
+    rc, out = orc.g1_add_be(g, g)
+    assert out.hex() == ("030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3"
+                         "15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4")
+    rc, out = orc.g1_mul_be(g, o.R.to_bytes(32, "big"))
+    assert rc == 1 and out == bytes(64)  # status 1 = ok-infinity (zisk.rs:144-172)
+
+
+def test_reference_pairing_vector_points_decode():
+    """G1/G2 points of test_ec_pairing_a (/root/reference/test/tests/levm/precompile_tests.rs:17-24) are on
+    curve under the x_im|x_re|y_im|y_re order; the out-of-range point of :143-151 is rejected with status 2."""
+    data = bytes.fromhex(
+        "1c76476f4def4bb94541d57ebba1193381ffa7aa76ada664dd31c16024c43f593034dd2920f673e204fee2811c678745fc819b55d3e9d294e45c9b03a76aef41"
+        "209dd15ebff5d46c4bd888e51a93cf99a7329636c63514396b4a452003a35bf704bf11ca01483bfa8b34b43561848d28905960114c8ac04049af4b6315a41678"
+        "2bb8324af6cfc93537a2ad1a445cfd0ca2a71acd7ac41fadbf933c2a51be344d120a2a4cf30c1bf9845f20c6fe39e07ea2cce61f0c9bb048165fe5e4de877550"
+        "111e129f1cf1097710d41c4ac70fcdfa5ba2023c6ff1cbeac322de49d1b6df7c2032c61a830e3c17286de9462bf242fca2883585b93870a73853face6a6bf411"
+        "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c21800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed"
+        "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa")
+    for off in (0, 192):
+        g1, g2 = data[off:off + 64], data[off + 64:off + 192]
+        assert o.g1_on_curve(o.g1_from_be(g1)) and o.g2_on_curve(o.g2_from_be(g2))
+        assert orc.g1_native_to_be(orc.g1_be_to_native(g1)) == g1
+        assert orc.g2_native_to_be(orc.g2_be_to_native(g2)) == g2
+    assert o.g2_from_be(data[192 + 64:384]) == o.G2_GEN
+    oob = (o.P + 1).to_bytes(32, "big") + (o.P + 2).to_bytes(32, "big")
+    with pytest.raises(ValueError, match="status 2"):
+        orc.g1_be_to_native(oob)
+    with pytest.raises(ValueError, match="status 3"):
+        orc.g1_be_to_native((1).to_bytes(32, "big") + (3).to_bytes(32, "big"))
+
+
+def test_field_core_vs_python():
+    rng = np.random.default_rng(7)
+    for field, mod in (("fq", o.P), ("fr", o.R)):
+        a = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(200)] + [0, 1, mod - 1]
+        b = [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(200)] + [mod - 1, mod - 1, mod - 1]
+        got = orc.array_to_ints(orc.field_mul(field, orc.ints_to_array(a), orc.ints_to_array(b)))
+        rinv = pow(o.MONT, -1, mod)
+        assert got == [x * y * rinv % mod for x, y in zip(a, b)]
+    x = orc.ints_to_array([5, o.R - 1, 0])
+    assert orc.array_to_ints(orc.fr_to_mont(x)) == [5 * o.MONT % o.R, (o.R - 1) * o.MONT % o.R, 0]
+    assert (orc.fr_from_mont(orc.fr_to_mont(x)) == x).all()
+
+
+def test_rand_and_chain_generators():
+    assert orc.array_to_ints(orc.rand_fr(o.SEED_SCALARS, 3, 9)) == [o.rand_fr(o.SEED_SCALARS, 3 + i) for i in range(9)]
+    k, d = o.chain_scalar(o.SEED_POINTS)
+    ref = o.chain_points(o._Fq, o.G1_GEN, o.SEED_POINTS, 50)
+    assert orc.g1_native_to_be(orc.g1_chain(50, k, d)) == b"".join(o.g1_to_be(p) for p in ref)
+    ref2 = o.chain_points(o._Fq2, o.G2_GEN, o.SEED_POINTS, 20)
+    assert orc.g2_native_to_be(orc.g2_chain(20, k, d)) == b"".join(o.g2_to_be(p) for p in ref2)
+
+
+def test_window_rule_is_arks():
+    # ark-ec 0.5.0: c = 3 if n < 32 else ln_without_floats(n) + 2  ->  10 / 15 / 18 at 2^12 / 2^20 / 2^24
+    assert [orc.lib().orc_msm_window(n) for n in (1, 31, 32, 1 << 12, 1 << 20, 1 << 24)] == [3, 3, 5, 10, 15, 18]
+
+
+def test_golden_ntt_2_12():
+    g = np.load(os.path.join(GOLD, "ntt_2_12.npz"))
+    a = orc.fr_to_mont(g["input_canonical"])
+    assert (orc.fr_from_mont(orc.fr_ntt(a, 12)) == g["forward_canonical"]).all()
+    assert (orc.fr_from_mont(orc.fr_ntt(a, 12, orc.NTT_COSET)) == g["coset5_forward_canonical"]).all()
+    assert (orc.fr_ntt(orc.fr_ntt(a, 12), 12, orc.NTT_INVERSE) == a).all()
+    assert (orc.fr_ntt(orc.fr_ntt(a, 12, orc.NTT_COSET), 12, orc.NTT_INVERSE | orc.NTT_COSET) == a).all()
+    assert (orc.fr_ntt(a, 12, threads=1) == orc.fr_ntt(a, 12, threads=4)).all()
+
+
+def test_golden_msm_2_12_and_small():
+    g = np.load(os.path.join(GOLD, "msm_g1_2_12.npz"))
+    pts = orc.g1_be_to_native(g["points_be"].tobytes())
+    for method in (0, 1):
+        assert orc.g1_msm(pts, g["scalars"], method) == g["result_be"].tobytes()
+    assert orc.g1_msm(pts, g["scalars"], 0, threads=1) == g["result_be"].tobytes()
+    k, d = o.chain_scalar(o.SEED_POINTS)
+    assert (pts == orc.g1_chain(4096, k, d)).all()
+    s = np.load(os.path.join(GOLD, "msm_small.npz"))
+    for m in (1, 2, 3, 31, 32, 33):
+        assert orc.g1_msm(pts[:m], s[f"g1_{m}_scalars"]) == s[f"g1_{m}_result"].tobytes(), m
+    p2 = orc.g2_be_to_native(s["g2_points_be"].tobytes())
+    for m in (1, 2, 33):
+        assert orc.g2_msm(p2[:m], s[f"g2_{m}_scalars"]) == s[f"g2_{m}_result"].tobytes(), m
+
+
+def test_ntt_small_sizes_vs_definition():
+    for lg in range(0, 7):
+        a = orc.rand_fr(o.SEED_NTT, 0, 1 << lg)
+        ai, am = orc.array_to_ints(a), orc.fr_to_mont(a)
+        for fl, kw in ((0, {}), (1, dict(inverse=True)), (2, dict(coset=5)), (3, dict(inverse=True, coset=5)), (2, dict(coset=11))):
+            got = orc.array_to_ints(orc.fr_from_mont(orc.fr_ntt(am, lg, fl, coset_gen=kw.get("coset"))))
+            assert got == o.ntt_direct(ai, **kw), (lg, fl)
+
+
+def test_msm_properties():
+    """size-independent properties used at full size on the GPU: linearity and the chain closed form."""
+    k, d = o.chain_scalar(o.SEED_POINTS)
+    n = 3000
+    pts = orc.g1_chain(n, k, d)
+    s, t = orc.rand_fr(1, 0, n), orc.rand_fr(2, 0, n)
+    st = orc.ints_to_array([(a + b) % o.R for a, b in zip(orc.array_to_ints(s), orc.array_to_ints(t))])
+    rc, summed = orc.g1_add_be(orc.g1_msm(pts, s), orc.g1_msm(pts, t))
+    assert summed == orc.g1_msm(pts, st)
+    dot = orc.chain_dot(s, k, d)
+    assert dot == sum(a * (k + i * d) for i, a in enumerate(orc.array_to_ints(s))) % o.R
+    assert orc.g1_mul_be(o.g1_to_be(o.G1_GEN), dot.to_bytes(32, "big"))[1] == orc.g1_msm(pts, s)
+    # edge distributions agree between Pippenger and the naive definition
+    for vals in ([0] * 64, [1] * 64, [o.R - 1] * 64, [o.R + 3] * 64, [(1 << 256) - 1] * 64):
+        sc = orc.ints_to_array(vals)
+        assert orc.g1_msm(pts[:64], sc, 0) == orc.g1_msm(pts[:64], sc, 1)
