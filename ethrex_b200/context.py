@@ -42,9 +42,13 @@ def _dev_ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_CUDA_STREAM_LEGACY = 0x1  # cudaStreamLegacy: the C ABI reserves NULL for "the context's own stream"
+
+
 def _current_stream_ptr():
+    """torch's current stream, so library work is ordered with the caller's tensors and events."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream or _CUDA_STREAM_LEGACY)
 
 
 class Context:

@@ -10,8 +10,10 @@
 //   2. scan_*        exclusive prefix sum of the histogram -> bucket offsets (3 small kernels);
 //   3. msm_scatter   recode again (cheaper than storing n*W digits) and drop each point index, with the
 //                    digit's sign in bit 31, into its bucket's slice of the sorted index array;
-//   4. msm_accumulate  THE hot kernel: one thread per bucket walks its slice, gathers 64/128-byte affine
-//                    bases with 128-bit loads and folds them into an XYZZ accumulator (8M+2S per point);
+//   4. msm_accumulate  THE hot kernel: one thread per SEGMENT (<= 64 consecutive entries of one bucket's slice)
+//                    gathers 64/128-byte affine bases with 128-bit loads, one ahead of the addition in
+//                    flight, and folds them into an XYZZ accumulator (8M+2S per point); partial_tree then
+//                    sums the partials of buckets that span several segments;
 //   5. bucket_chunk / bucket_tree  sum_b (b+1)*B_b per window: running sums over chunks of 32 buckets, then a
 //                    log-depth pairwise tree carrying (sum, weighted sum) -- no serial 2^(c-1) loop anywhere;
 //   6. msm_horner    sum_w 2^(c*w) * S_w in one thread (W*c doublings), leaving one XYZZ partial sum.
@@ -33,8 +35,9 @@ struct MsmPlan {
 static MsmPlan make_plan(size_t n, uint32_t forced_c) {
   uint32_t lg = 0;
   while (((size_t)1 << lg) < n) ++lg;
+  // measured on B200 (profiles/): c = 16 is best for 2^18..2^22 points, 17 from 2^23 up; below that lg-4
   uint32_t c = forced_c ? forced_c : (lg > 8 ? lg - 4 : 4);
-  if (!forced_c && c > 20) c = 20;
+  if (!forced_c && c > 16) c = lg >= 23 ? 17 : 16;
   if (c < 2) c = 2;
   if (c > 24) c = 24;
   MsmPlan p;
@@ -126,12 +129,15 @@ __global__ void __launch_bounds__(256) msm_scatter(const void* scalars, size_t n
 // ---- exclusive scan of the histogram (G entries) ---------------------------------------------------------
 static constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, size_t G, uint32_t* tile_sums) {
+// seg > 0: scan ceil(in[i] / seg) instead of in[i] (number of length-`seg` segments of each bucket)
+B2_D uint32_t scan_value(uint32_t v, uint32_t seg) { return seg ? (v + seg - 1) / seg : v; }
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, size_t G, uint32_t seg, uint32_t* tile_sums) {
   __shared__ uint32_t red[kScanThreads / 32];
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += in[base + k];
+  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += scan_value(in[base + k], seg);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -166,12 +172,12 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets(uint32_t* tile_sums, s
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, size_t G, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, size_t G, uint32_t seg, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
   __shared__ uint32_t warp_tot[kScanThreads / 32];
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems], s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? in[base + k] : 0; s += v[k]; }
+  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? scan_value(in[base + k], seg) : 0; s += v[k]; }
   uint32_t incl = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += t; }
@@ -182,41 +188,86 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, s
   uint32_t run = tile_offsets[blockIdx.x] + wbase + incl - s;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    if (base + k < G) { offsets[base + k] = run; cursor[base + k] = run; }
+    if (base + k < G) { offsets[base + k] = run; if (cursor) cursor[base + k] = run; }
     run += v[k];
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) offsets[G] = run;  // total
 }
 
 // ---- bucket accumulation ----------------------------------------------------------------------------------
+// Buckets are wildly uneven even for uniform scalars (the top window of a 254-bit scalar only has
+// 254 - (W-1)c bits, and real witnesses are full of 0/1 values), so the unit of work is a SEGMENT: at most
+// kSegLen consecutive entries of one bucket's slice.  seg_off = exclusive scan of ceil(count/kSegLen); thread s
+// finds its bucket by binary search, folds its <= kSegLen points into an XYZZ partial and records the bucket id.
+// partial_tree then sums the partials of multi-segment buckets with a radix-kTreeRadix tree in place, leaving
+// each bucket's total in its first partial.
+static constexpr uint32_t kSegLen = 64;
+static constexpr uint32_t kTreeRadix = 64;
+
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
-                                                      const uint32_t* __restrict__ offsets, size_t G, void* __restrict__ buckets) {
-  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  uint32_t lo = offsets[g], hi = offsets[g + 1];
+                                                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ seg_off,
+                                                      uint32_t G, void* __restrict__ partials, uint32_t* __restrict__ seg_bucket) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= __ldg(seg_off + G)) return;
+  // largest g with seg_off[g] <= s  (empty buckets repeat offsets, so take the upper bound)
+  uint32_t lo_g = 0, hi_g = G;
+  while (hi_g - lo_g > 1) {
+    uint32_t mid = (lo_g + hi_g) >> 1;
+    if (__ldg(seg_off + mid) <= s) lo_g = mid; else hi_g = mid;
+  }
+  const uint32_t g = lo_g;
+  const uint32_t j = s - __ldg(seg_off + g);
+  uint32_t lo = __ldg(offsets + g) + j * kSegLen, end = __ldg(offsets + g + 1);
+  uint32_t hi = lo + kSegLen < end ? lo + kSegLen : end;
   XYZZ<F> acc = XYZZ<F>::identity();
+  uint32_t v = __ldg(idx + lo);
+  Affine<F> p = load_affine_nc<F>(points, v & 0x7fffffffu);
   for (uint32_t e = lo; e < hi; ++e) {
-    uint32_t v = __ldg(idx + e);
-    Affine<F> p = load_affine_nc<F>(points, v & 0x7fffffffu);
+    // software prefetch: issue the next gather before the ~1500-instruction addition
+    uint32_t vn = v; Affine<F> pn = p;
+    if (e + 1 < hi) { vn = __ldg(idx + e + 1); pn = load_affine_nc<F>(points, vn & 0x7fffffffu); }
     if (v >> 31) p.y = F::neg(p.y);
     xyzz_add_mixed(acc, p.x, p.y);
+    v = vn; p = pn;
   }
-  store_xyzz(buckets, g, acc);
+  store_xyzz(partials, s, acc);
+  seg_bucket[s] = g;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) partial_tree(const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ seg_bucket, uint32_t G,
+                                                    uint32_t stride, void* __restrict__ partials) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= __ldg(seg_off + G)) return;
+  const uint32_t g = seg_bucket[s];
+  const uint32_t base = __ldg(seg_off + g), ns = __ldg(seg_off + g + 1) - base, j = s - base;
+  if (ns <= stride || (j % (stride * kTreeRadix)) != 0) return;
+  XYZZ<F> acc = load_xyzz<F>(partials, s);
+  for (uint32_t t = 1; t < kTreeRadix; ++t) {
+    uint32_t jj = j + t * stride;
+    if (jj >= ns) break;
+    XYZZ<F> q = load_xyzz<F>(partials, s + t * stride);
+    xyzz_add(acc, q);
+  }
+  store_xyzz(partials, s, acc);
 }
 
 // ---- bucket reduction: S_w = sum_b (b+1) * B[w][b] ---------------------------------------------------------
 // chunk j of window w: S = sum B, V = sum_k (k+1) * B[j*chunk + k]
 template <class F>
-__global__ void __launch_bounds__(128) bucket_chunk(const void* __restrict__ buckets, MsmPlan pl, void* __restrict__ chunkS, void* __restrict__ chunkV) {
+__global__ void __launch_bounds__(128) bucket_chunk(const void* __restrict__ partials, const uint32_t* __restrict__ seg_off, MsmPlan pl, void* __restrict__ chunkS, void* __restrict__ chunkV) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t total = (size_t)pl.W * pl.T;
   if (t >= total) return;
   size_t first = t * pl.chunk;  // bucket arrays are [w][b] contiguous and T*chunk == B
   XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
   for (int k = (int)pl.chunk - 1; k >= 0; --k) {
-    XYZZ<F> b = load_xyzz<F>(buckets, first + k);
-    xyzz_add(run, b);
+    uint32_t so = __ldg(seg_off + first + k);
+    if (__ldg(seg_off + first + k + 1) != so) {  // non-empty bucket: its total sits in its first partial
+      XYZZ<F> b = load_xyzz<F>(partials, so);
+      xyzz_add(run, b);
+    }
     xyzz_add(acc, run);
   }
   store_xyzz(chunkS, t, run);
@@ -305,7 +356,10 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_TRY(ensure(ctx, ctx->ws_cursor, G * 4));
   B2_TRY(ensure(ctx, ctx->ws_blocksums, tiles * 4));
   B2_TRY(ensure(ctx, ctx->ws_idx, n * (size_t)pl.W * 4));
-  B2_TRY(ensure(ctx, ctx->ws_buckets, G * xy));
+  const size_t S_max = (n * (size_t)pl.W) / kSegLen + G;  // upper bound on the number of segments
+  B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));     // segment partials (bucket totals after partial_tree)
+  B2_TRY(ensure(ctx, ctx->ws_segoff, (G + 1) * 4));
+  B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
   B2_TRY(ensure(ctx, ctx->ws_chunkS, (size_t)pl.W * pl.T * xy));
   B2_TRY(ensure(ctx, ctx->ws_chunkV, (size_t)pl.W * pl.T * xy));
   uint32_t* hist = (uint32_t*)ctx->ws_hist.p;
@@ -319,16 +373,27 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
   B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist);
   phase_mark(ctx, 1, st);
-  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, G, tsum);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, G, 0u, tsum);
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
-  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, G, tsum, offsets, cursor);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, G, 0u, tsum, offsets, cursor);
+  uint32_t* seg_off = (uint32_t*)ctx->ws_segoff.p;
+  uint32_t* seg_bucket = (uint32_t*)ctx->ws_segbucket.p;
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, G, kSegLen, tsum);
+  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, G, kSegLen, tsum, seg_off, (uint32_t*)nullptr);
   phase_mark(ctx, 2, st);
   B2_LAUNCH(ctx, msm_scatter, sgrid, 256, 0, st, d_scalars, n, flags, pl, cursor, idx);
   phase_mark(ctx, 3, st);
-  B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((G + 127) / 128), 128, 0, st, d_points, idx, offsets, G, ctx->ws_buckets.p);
+  B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, d_points, idx, offsets, seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
+  {
+    // worst case every point of a window lands in one bucket: ceil(n / kSegLen) partials to fold
+    size_t worst = (n + kSegLen - 1) / kSegLen;
+    for (size_t stride = 1; stride < worst; stride *= kTreeRadix)
+      B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, seg_off, seg_bucket, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
+  }
   phase_mark(ctx, 4, st);
   const size_t chunks = (size_t)pl.W * pl.T;
-  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, seg_off, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
   uint32_t chunk_log2 = 0;
   while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
   for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {

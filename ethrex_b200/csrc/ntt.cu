@@ -240,7 +240,8 @@ static Plan make_ntt_plan(uint32_t k) {
   }
   if (!p.P) {
     if (k <= (uint32_t)kMaxStage) { p.P = 1; p.s[0] = k; }
-    else if (k <= 24) { p.P = 2; p.s[0] = (k + 1) / 2; p.s[1] = k - p.s[0]; }
+    // measured on B200: 64 KiB tiles (several CTAs per SM) beat 128 KiB ones, so stages are capped at 10-11
+    else if (k <= 20) { p.P = 2; p.s[0] = (k + 1) / 2; p.s[1] = k - p.s[0]; }
     else { p.P = 3; p.s[0] = (k + 2) / 3; p.s[1] = (k - p.s[0] + 1) / 2; p.s[2] = k - p.s[0] - p.s[1]; }
   }
   uint32_t tile_log = 11;  // 2048 elements = 64 KiB per CTA by default

@@ -108,7 +108,8 @@ int b200zk_g2_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars
                            uint8_t out[128]);
 
 /* ---- device-pointer entry points: inputs already in HBM (native formats only) ------------------------- */
-/* `stream`: a cudaStream_t passed as void*; NULL = the context's own stream.  The *_device calls enqueue
+/* `stream`: a cudaStream_t passed as void*; NULL = the context's own (non-blocking) stream, so pass
+ * cudaStreamLegacy ((void*)0x1) to mean the legacy default stream.  The *_device calls enqueue
  * every kernel on that stream, then copy the 64/128-byte result to `out` and wait for it. */
 int b200zk_g1_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
                          uint32_t flags, void* stream, uint8_t out[64]);
