@@ -164,7 +164,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->ws_hist, &ctx->ws_offsets, &ctx->ws_cursor, &ctx->ws_blocksums, &ctx->ws_idx, &ctx->ws_buckets, &ctx->ws_chunkS,
-                    &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket};
+                    &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   for (auto& kv : ctx->twiddles) cudaFree(kv.second.d);
   for (auto& kv : ctx->bases) cudaFree(kv.second.d);

@@ -42,7 +42,7 @@ struct b200zk_ctx {
   cudaEvent_t ev[8] = {};
   // grow-only workspaces
   b200zk::DevBuf ws_hist, ws_offsets, ws_cursor, ws_blocksums, ws_idx, ws_buckets, ws_chunkS, ws_chunkV, ws_result,
-      ws_points, ws_scalars, ws_ntt, ws_misc, ws_out, ws_segoff, ws_segbucket;
+      ws_points, ws_scalars, ws_ntt, ws_misc, ws_out, ws_segoff, ws_segbucket, ws_digits;
   std::map<uint64_t, b200zk::TwiddleSet> twiddles;
   std::map<uint64_t, b200zk::BasesEntry> bases;
   uint64_t next_handle = 1;

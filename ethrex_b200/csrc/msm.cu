@@ -5,15 +5,15 @@
 // (SURVEY.md section 8a rows a6/a7).  Same digit rule as ark's `make_digits` (signed radix-2^c digits, carry
 // when the window value >= 2^(c-1), 2^(c-1) buckets per window), but the schedule is GPU shaped:
 //
-//   1. msm_hist      one thread per scalar: recode into W signed digits, histogram (window,bucket) with
-//                    spread global atomics (the W*2^(c-1) counters live in L2);
-//   2. scan_*        exclusive prefix sum of the histogram -> bucket offsets (3 small kernels);
-//   3. msm_scatter   recode again (cheaper than storing n*W digits) and drop each point index, with the
-//                    digit's sign in bit 31, into its bucket's slice of the sorted index array;
-//   4. msm_accumulate  THE hot kernel: one thread per SEGMENT (<= 64 consecutive entries of one bucket's slice)
+//   1. msm_hist      one thread per scalar: recode into W signed digits, store them window-major, histogram
+//                    (window,bucket) with warp-aggregated global atomics (the W*2^(c-1) counters live in L2);
+//   2. scan_*        exclusive prefix sums -> bucket offsets and segment offsets (3 small kernels each);
+//   3. msm_scatter   walk the digits window by window and drop each point index, with the digit's sign in
+//                    bit 31, into its bucket's slice of the sorted index array (one window's slice is L2 sized);
+//   4. msm_accumulate  THE hot kernel: one thread per fixed SLICE of 256 sorted entries (perfectly balanced):
 //                    gathers 64/128-byte affine bases with 128-bit loads, one ahead of the addition in
-//                    flight, and folds them into an XYZZ accumulator (8M+2S per point); partial_tree then
-//                    sums the partials of buckets that span several segments;
+//                    flight, folds them into an XYZZ accumulator (8M+2S per point) and closes a run at every
+//                    bucket boundary; partial_tree then sums the runs of buckets that have more than one;
 //   5. bucket_chunk / bucket_tree  sum_b (b+1)*B_b per window: running sums over chunks of 32 buckets, then a
 //                    log-depth pairwise tree carrying (sum, weighted sum) -- no serial 2^(c-1) loop anywhere;
 //   6. msm_horner    sum_w 2^(c*w) * S_w in one thread (W*c doublings), leaving one XYZZ partial sum.
@@ -92,52 +92,79 @@ B2_D uint32_t window_bits(const uint32_t s[8], uint32_t w, uint32_t c) {
   return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
-// Calls f(w, bucket_index_0based, negative) for every non-zero signed digit of the scalar.
-template <class Fn> B2_D void for_each_digit(const uint32_t s[8], const MsmPlan& pl, Fn f) {
-  uint32_t carry = 0;
-  for (uint32_t w = 0; w < pl.W; ++w) {
-    uint32_t coef = window_bits(s, w, pl.c) + carry;
-    carry = 0;
-    bool neg = false;
-    uint32_t mag = coef;
-    if (w + 1 < pl.W && coef >= pl.B) {  // ark make_digits: carry = (coef + radix/2) >> c
-      carry = 1; neg = true; mag = (1u << pl.c) - coef;
+// Digit codes: bucket index (0-based) | sign << 31, or kNoDigit for a zero digit.  msm_hist stores them
+// window-major (digits[w*n + i]) so that msm_scatter can walk ONE window at a time: all of a window's random
+// 4-byte writes then land in that window's slice of idx (n*4 bytes = 64 MiB at 2^24, L2 resident) instead of
+// being spread over the whole n*W*4-byte array.
+static constexpr uint32_t kNoDigit = 0xffffffffu;
+
+// One atomic per distinct key per warp: hot buckets (top window, scalars 0/1/small) would otherwise serialise
+// 32 atomics on one L2 address.  Returns the warp-wide count of `key` and this lane's rank within its group.
+B2_D uint32_t warp_group(uint32_t key, bool active, uint32_t* rank, uint32_t* group_mask) {
+  uint32_t mask = __match_any_sync(__activemask(), active ? key : kNoDigit);
+  uint32_t lane = threadIdx.x & 31;
+  *rank = __popc(mask & ((1u << lane) - 1u));
+  *group_mask = mask;
+  return __popc(mask);
+}
+
+__global__ void __launch_bounds__(256) msm_hist(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* hist, uint32_t* digits) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t s[8];
+    load_scalar(scalars, i, flags, s);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < pl.W; ++w) {
+      uint32_t coef = window_bits(s, w, pl.c) + carry;
+      carry = 0;
+      uint32_t neg = 0, mag = coef;
+      if (w + 1 < pl.W && coef >= pl.B) { carry = 1; neg = 0x80000000u; mag = (1u << pl.c) - coef; }  // ark make_digits rule
+      uint32_t code = mag ? ((mag - 1) | neg) : kNoDigit;
+      digits[(size_t)w * n + i] = code;
+      uint32_t rank, gm;
+      uint32_t cnt = warp_group(mag - 1, mag != 0, &rank, &gm);
+      if (mag && rank == 0) atomicAdd(&hist[(size_t)w * pl.B + (mag - 1)], cnt);
     }
-    if (mag) f(w, mag - 1, neg);
   }
 }
 
-__global__ void __launch_bounds__(256) msm_hist(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* hist) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    uint32_t s[8];
-    load_scalar(scalars, i, flags, s);
-    for_each_digit(s, pl, [&](uint32_t w, uint32_t b, bool) { atomicAdd(&hist[(size_t)w * pl.B + b], 1u); });
-  }
-}
-
-__global__ void __launch_bounds__(256) msm_scatter(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* cursor, uint32_t* idx) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    uint32_t s[8];
-    load_scalar(scalars, i, flags, s);
-    for_each_digit(s, pl, [&](uint32_t w, uint32_t b, bool neg) {
-      uint32_t pos = atomicAdd(&cursor[(size_t)w * pl.B + b], 1u);
-      idx[pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
-    });
+__global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ digits, size_t n, MsmPlan pl, uint32_t* cursor, uint32_t* idx) {
+  const size_t total = (size_t)pl.W * n;
+  // whole warps stay in the loop together (total is padded per warp) so the match/shuffle below is convergent
+  const size_t total_pad = (total + 31) & ~(size_t)31;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total_pad; t += (size_t)gridDim.x * blockDim.x) {
+    uint32_t code = t < total ? __ldg(digits + t) : kNoDigit;
+    bool active = code != kNoDigit;
+    size_t w = t / n;  // a warp may straddle two windows at the seam: key on the global bucket id
+    uint32_t g = (uint32_t)(w * pl.B) + (code & 0x7fffffffu);
+    uint32_t rank, mask;
+    uint32_t cnt = warp_group(g, active, &rank, &mask);
+    uint32_t base = 0;
+    if (active && rank == 0) base = atomicAdd(&cursor[g], cnt);
+    // broadcast the leader's base to its group: leader = lowest lane of the group
+    base = __shfl_sync(mask, base, __ffs(mask) - 1);
+    if (active) idx[base + rank] = (uint32_t)(t - w * n) | (code & 0x80000000u);
   }
 }
 
 // ---- exclusive scan of the histogram (G entries) ---------------------------------------------------------
 static constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
 
-// seg > 0: scan ceil(in[i] / seg) instead of in[i] (number of length-`seg` segments of each bucket)
-B2_D uint32_t scan_value(uint32_t v, uint32_t seg) { return seg ? (v + seg - 1) / seg : v; }
+// seg == 0: scan the counts themselves (-> bucket offsets).
+// seg  > 0: scan the flag "bucket i is non-empty and does not start on a multiple of seg" (aux = bucket offsets);
+//           scan_apply then adds ceil(offset/seg), giving run_off[i] = index of the first RUN of bucket i when the
+//           sorted entries are cut at every multiple of seg and at every bucket start (see msm_accumulate).
+B2_D uint32_t scan_value(const uint32_t* in, const uint32_t* aux, size_t i, uint32_t seg) {
+  uint32_t v = in[i];
+  if (!seg) return v;
+  return (v != 0 && (aux[i] % seg) != 0) ? 1u : 0u;
+}
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, size_t G, uint32_t seg, uint32_t* tile_sums) {
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, const uint32_t* aux, size_t G, uint32_t seg, uint32_t* tile_sums) {
   __shared__ uint32_t red[kScanThreads / 32];
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += scan_value(in[base + k], seg);
+  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += scan_value(in, aux, base + k, seg);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -172,12 +199,12 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets(uint32_t* tile_sums, s
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, size_t G, uint32_t seg, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, const uint32_t* aux, size_t G, uint32_t seg, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
   __shared__ uint32_t warp_tot[kScanThreads / 32];
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems], s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? scan_value(in[base + k], seg) : 0; s += v[k]; }
+  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? scan_value(in, aux, base + k, seg) : 0; s += v[k]; }
   uint32_t incl = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += t; }
@@ -188,51 +215,81 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, s
   uint32_t run = tile_offsets[blockIdx.x] + wbase + incl - s;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    if (base + k < G) { offsets[base + k] = run; if (cursor) cursor[base + k] = run; }
+    if (base + k < G) { offsets[base + k] = seg ? run + (aux[base + k] + seg - 1) / seg : run; if (cursor) cursor[base + k] = run; }
     run += v[k];
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) offsets[G] = run;  // total
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) offsets[G] = seg ? run + (aux[G] + seg - 1) / seg : run;  // total
 }
 
 // ---- bucket accumulation ----------------------------------------------------------------------------------
 // Buckets are wildly uneven even for uniform scalars (the top window of a 254-bit scalar only has
-// 254 - (W-1)c bits, and real witnesses are full of 0/1 values), so the unit of work is a SEGMENT: at most
-// kSegLen consecutive entries of one bucket's slice.  seg_off = exclusive scan of ceil(count/kSegLen); thread s
-// finds its bucket by binary search, folds its <= kSegLen points into an XYZZ partial and records the bucket id.
-// partial_tree then sums the partials of multi-segment buckets with a radix-kTreeRadix tree in place, leaving
-// each bucket's total in its first partial.
-static constexpr uint32_t kSegLen = 64;
+// 254 - (W-1)c bits, and real witnesses are full of 0/1 values), so work is NOT split by bucket.  The sorted
+// entry array is cut into fixed slices of kSegLen entries, one per thread: every thread performs exactly
+// kSegLen gathers + mixed additions, whatever the bucket sizes.  Inside its slice a thread closes a RUN (stores
+// the XYZZ partial and its bucket id) whenever the bucket changes.  Runs are numbered along the sorted order:
+// a run starts at every multiple of kSegLen and at every bucket start, so the first run of bucket g is
+//   run_off[g] = ceil(offsets[g]/kSegLen) + #{non-empty g' < g : offsets[g'] % kSegLen != 0}     (scan, seg mode)
+// and a thread derives its first slot from the same formula.  partial_tree then folds the runs of every bucket
+// that has more than one (a bucket straddling a slice boundary, or a heavy bucket spanning many slices) with a
+// radix-kTreeRadix tree in place, leaving each bucket's total in its first run.
+static constexpr uint32_t kSegLen = 256;
 static constexpr uint32_t kTreeRadix = 64;
+
+// largest g in [lo, G) with offsets[g] <= e, given offsets[lo] <= e: gallop then bisect (the next non-empty
+// bucket is almost always within a few entries; empty buckets repeat the same offset and are skipped)
+B2_D uint32_t bucket_of(const uint32_t* __restrict__ offsets, uint32_t G, uint32_t lo, uint32_t e) {
+  uint32_t step = 1, hi = lo + 1;
+  while (hi < G && __ldg(offsets + hi) <= e) { lo = hi; step <<= 1; hi = lo + step; }
+  if (hi > G) hi = G;
+  // invariant: offsets[lo] <= e, and (hi == G or offsets[hi] > e)
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
-                                                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ seg_off,
-                                                      uint32_t G, void* __restrict__ partials, uint32_t* __restrict__ seg_bucket) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= __ldg(seg_off + G)) return;
-  // largest g with seg_off[g] <= s  (empty buckets repeat offsets, so take the upper bound)
-  uint32_t lo_g = 0, hi_g = G;
-  while (hi_g - lo_g > 1) {
-    uint32_t mid = (lo_g + hi_g) >> 1;
-    if (__ldg(seg_off + mid) <= s) lo_g = mid; else hi_g = mid;
+                                                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ run_off,
+                                                      uint32_t G, void* __restrict__ partials, uint32_t* __restrict__ run_bucket) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t M = __ldg(offsets + G);
+  const uint64_t e0_64 = (uint64_t)t * kSegLen;
+  if (e0_64 >= M) return;
+  const uint32_t e0 = (uint32_t)e0_64;
+  const uint32_t e1 = (M - e0 > kSegLen) ? e0 + kSegLen : M;
+  // full binary search once per thread
+  uint32_t g;
+  {
+    uint32_t lo = 0, hi = G;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= e0) lo = mid; else hi = mid; }
+    g = lo;
   }
-  const uint32_t g = lo_g;
-  const uint32_t j = s - __ldg(seg_off + g);
-  uint32_t lo = __ldg(offsets + g) + j * kSegLen, end = __ldg(offsets + g + 1);
-  uint32_t hi = lo + kSegLen < end ? lo + kSegLen : end;
+  const uint32_t off0 = __ldg(offsets + g);
+  uint32_t slot = t + (__ldg(run_off + g) - (off0 + kSegLen - 1) / kSegLen) + ((off0 % kSegLen) ? 1u : 0u);
+  uint32_t next = __ldg(offsets + g + 1);  // first entry of the following bucket (> e0)
   XYZZ<F> acc = XYZZ<F>::identity();
-  uint32_t v = __ldg(idx + lo);
+  uint32_t v = __ldg(idx + e0);
   Affine<F> p = load_affine_nc<F>(points, v & 0x7fffffffu);
-  for (uint32_t e = lo; e < hi; ++e) {
+  for (uint32_t e = e0; e < e1; ++e) {
     // software prefetch: issue the next gather before the ~1500-instruction addition
     uint32_t vn = v; Affine<F> pn = p;
-    if (e + 1 < hi) { vn = __ldg(idx + e + 1); pn = load_affine_nc<F>(points, vn & 0x7fffffffu); }
+    if (e + 1 < e1) { vn = __ldg(idx + e + 1); pn = load_affine_nc<F>(points, vn & 0x7fffffffu); }
+    if (e == next) {  // bucket boundary: close the run
+      store_xyzz(partials, slot, acc);
+      run_bucket[slot] = g;
+      ++slot;
+      acc = XYZZ<F>::identity();
+      g = bucket_of(offsets, G, g + 1, e);
+      next = __ldg(offsets + g + 1);
+    }
     if (v >> 31) p.y = F::neg(p.y);
     xyzz_add_mixed(acc, p.x, p.y);
     v = vn; p = pn;
   }
-  store_xyzz(partials, s, acc);
-  seg_bucket[s] = g;
+  store_xyzz(partials, slot, acc);
+  run_bucket[slot] = g;
 }
 
 template <class F>
@@ -348,6 +405,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   }
   if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
   const MsmPlan pl = make_plan(n, ctx->msm_window);
+  if ((unsigned long long)n * pl.W >= (1ull << 32)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32 (shard the MSM)");
   const size_t G = (size_t)pl.W * pl.B;
   const size_t tiles = (G + kScanTile - 1) / kScanTile;
   const size_t xy = 4 * FieldBytes<F>::value;
@@ -356,7 +414,9 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_TRY(ensure(ctx, ctx->ws_cursor, G * 4));
   B2_TRY(ensure(ctx, ctx->ws_blocksums, tiles * 4));
   B2_TRY(ensure(ctx, ctx->ws_idx, n * (size_t)pl.W * 4));
-  const size_t S_max = (n * (size_t)pl.W) / kSegLen + G;  // upper bound on the number of segments
+  B2_TRY(ensure(ctx, ctx->ws_digits, n * (size_t)pl.W * 4));
+  const size_t S_max = (n * (size_t)pl.W) / kSegLen + 1 + G;  // upper bound on the number of runs
+  const size_t slices = (n * (size_t)pl.W + kSegLen - 1) / kSegLen;
   B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));     // segment partials (bucket totals after partial_tree)
   B2_TRY(ensure(ctx, ctx->ws_segoff, (G + 1) * 4));
   B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
@@ -371,23 +431,25 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   phase_mark(ctx, 0, st);
   B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
   const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
-  B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist);
+  uint32_t* digits = (uint32_t*)ctx->ws_digits.p;
+  B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist, digits);
   phase_mark(ctx, 1, st);
-  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, G, 0u, tsum);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, tsum);
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
-  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, G, 0u, tsum, offsets, cursor);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, tsum, offsets, cursor);
   uint32_t* seg_off = (uint32_t*)ctx->ws_segoff.p;
   uint32_t* seg_bucket = (uint32_t*)ctx->ws_segbucket.p;
-  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, G, kSegLen, tsum);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)offsets, G, kSegLen, tsum);
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
-  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, G, kSegLen, tsum, seg_off, (uint32_t*)nullptr);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)offsets, G, kSegLen, tsum, seg_off, (uint32_t*)nullptr);
   phase_mark(ctx, 2, st);
-  B2_LAUNCH(ctx, msm_scatter, sgrid, 256, 0, st, d_scalars, n, flags, pl, cursor, idx);
+  const unsigned wgrid = (unsigned)std::min<size_t>((n * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
+  B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, st, (const uint32_t*)digits, n, pl, cursor, idx);
   phase_mark(ctx, 3, st);
-  B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, d_points, idx, offsets, seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
+  B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((slices + 127) / 128), 128, 0, st, d_points, idx, offsets, seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
   {
-    // worst case every point of a window lands in one bucket: ceil(n / kSegLen) partials to fold
-    size_t worst = (n + kSegLen - 1) / kSegLen;
+    // worst case every point of a window lands in one bucket: ceil(n / kSegLen) + 1 runs to fold
+    size_t worst = (n + kSegLen - 1) / kSegLen + 1;
     for (size_t stride = 1; stride < worst; stride *= kTreeRadix)
       B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, seg_off, seg_bucket, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
   }

@@ -77,7 +77,7 @@ def main():
     if "msm" in sections:
         import pyref
         k, dd = pyref.chain_scalar(pyref.SEED_POINTS)
-        for log_n, windows in ((20, (0, 11, 12, 13, 14, 15, 16)), (24, (0, 14, 15, 16, 17, 18, 20))):
+        for log_n, windows in ((20, (0, 11, 12, 13, 14, 15, 16)), (24, (0, 16, 17, 18, 19, 20, 21))):
             n = 1 << log_n
             p, s = dev(8 * n), dev(4 * n)
             t0 = time.time()
