@@ -42,7 +42,12 @@ SIGNATURES = {
     "b200zk_fr_ntt": (_int, [_ctx, _vp, _u32, _u32, _vp]),
     "b200zk_g1_bases_upload": (_int, [_ctx, _vp, _sz, _u32, C.POINTER(_u64)]),
     "b200zk_g2_bases_upload": (_int, [_ctx, _vp, _sz, _u32, C.POINTER(_u64)]),
+    "b200zk_g1_bases_from_device": (_int, [_ctx, _vp, _sz, _vp, C.POINTER(_u64)]),
+    "b200zk_g2_bases_from_device": (_int, [_ctx, _vp, _sz, _vp, C.POINTER(_u64)]),
+    "b200zk_bases_precompute": (_int, [_ctx, _u64, _u32]),
     "b200zk_bases_free": (_int, [_ctx, _u64]),
+    "b200zk_g1_msm_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
+    "b200zk_g2_msm_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g1_msm_resident": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp]),
     "b200zk_g2_msm_resident": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp]),
     "b200zk_g1_msm_device": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
@@ -52,6 +57,8 @@ SIGNATURES = {
     "b200zk_fr_ntt_device": (_int, [_ctx, _vp, _u32, _u32, _vp, _vp]),
     "b200zk_g1_msm_partial_device": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g2_msm_partial_device": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
+    "b200zk_g1_msm_partial_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
+    "b200zk_g2_msm_partial_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g1_fold_partials_device": (_int, [_ctx, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g2_fold_partials_device": (_int, [_ctx, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_field_to_mont_device": (_int, [_ctx, _vp, _sz, _int, _vp]),

@@ -137,6 +137,30 @@ class Context:
         self._check(F.lib.b200zk_g2_bases_upload(self._h, pp, n, flags, C.byref(h)), "b200zk_g2_bases_upload")
         return h.value
 
+    def g1_bases_from_device(self, d_points, n: int) -> int:
+        h = C.c_uint64()
+        self._check(F.lib.b200zk_g1_bases_from_device(self._h, _dev_ptr(d_points), n, _current_stream_ptr(), C.byref(h)), "b200zk_g1_bases_from_device")
+        return h.value
+
+    def g2_bases_from_device(self, d_points, n: int) -> int:
+        h = C.c_uint64()
+        self._check(F.lib.b200zk_g2_bases_from_device(self._h, _dev_ptr(d_points), n, _current_stream_ptr(), C.byref(h)), "b200zk_g2_bases_from_device")
+        return h.value
+
+    def bases_precompute(self, handle: int, window_bits: int = 0):
+        """One-off: expand resident bases into their window multiples 2^(c*w)*P_i (fewer additions per MSM)."""
+        self._check(F.lib.b200zk_bases_precompute(self._h, handle, window_bits), "b200zk_bases_precompute")
+
+    def g1_msm_resident_device(self, handle: int, d_scalars, n: int, flags: int = 0) -> bytes:
+        out = C.create_string_buffer(64)
+        self._check(F.lib.b200zk_g1_msm_resident_device(self._h, handle, _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), out), "b200zk_g1_msm_resident_device")
+        return out.raw
+
+    def g2_msm_resident_device(self, handle: int, d_scalars, n: int, flags: int = 0) -> bytes:
+        out = C.create_string_buffer(128)
+        self._check(F.lib.b200zk_g2_msm_resident_device(self._h, handle, _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), out), "b200zk_g2_msm_resident_device")
+        return out.raw
+
     def bases_free(self, handle: int):
         self._check(F.lib.b200zk_bases_free(self._h, handle), "b200zk_bases_free")
 
@@ -178,6 +202,12 @@ class Context:
 
     def g2_msm_partial_device(self, d_points, d_scalars, n: int, d_partial, flags: int = 0):
         self._check(F.lib.b200zk_g2_msm_partial_device(self._h, _dev_ptr(d_points), _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g2_msm_partial_device")
+
+    def g1_msm_partial_resident_device(self, handle: int, d_scalars, n: int, d_partial, flags: int = 0):
+        self._check(F.lib.b200zk_g1_msm_partial_resident_device(self._h, handle, _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g1_msm_partial_resident_device")
+
+    def g2_msm_partial_resident_device(self, handle: int, d_scalars, n: int, d_partial, flags: int = 0):
+        self._check(F.lib.b200zk_g2_msm_partial_resident_device(self._h, handle, _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g2_msm_partial_resident_device")
 
     def g1_fold_partials_device(self, d_partials, count: int, flags: int = 0) -> bytes:
         out = C.create_string_buffer(64)

@@ -27,20 +27,22 @@ int read_result(b200zk_ctx* ctx, const void* d_out, size_t bytes, cudaStream_t s
 }
 
 template <bool G2>
-int msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_out) {
+int msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_out,
+                     uint32_t table_c = 0, size_t table_stride = 0) {
   if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
   B2_TRY(ensure(ctx, ctx->ws_result, 256));
-  if (G2) { B2_TRY(msm_run_g2(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p)); return msm_encode_g2(ctx, ctx->ws_result.p, 1, flags, st, d_out); }
-  B2_TRY(msm_run_g1(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p));
+  if (G2) { B2_TRY(msm_run_g2(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p, table_c, table_stride)); return msm_encode_g2(ctx, ctx->ws_result.p, 1, flags, st, d_out); }
+  B2_TRY(msm_run_g1(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p, table_c, table_stride));
   return msm_encode_g1(ctx, ctx->ws_result.p, 1, flags, st, d_out);
 }
 
 template <bool G2>
-int msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t* out) {
+int msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t* out,
+               uint32_t table_c = 0, size_t table_stride = 0) {
   if (!ctx || !out || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   B2_TRY(ensure(ctx, ctx->ws_out, 256));
-  B2_TRY(msm_device_async<G2>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p));
+  B2_TRY(msm_device_async<G2>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p, table_c, table_stride));
   return read_result(ctx, ctx->ws_out.p, Sizes<G2>::point, st, out);
 }
 
@@ -96,7 +98,31 @@ int msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n
   if (it == ctx->bases.end() || it->second.g2 != G2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: n exceeds the resident bases");
   B2_TRY(stage_scalars(ctx, scalars, n, ctx->stream));
-  return msm_device<G2>(ctx, it->second.d, ctx->ws_scalars.p, n, flags & ~B200ZK_POINTS_BE, ctx->stream, out);
+  return msm_device<G2>(ctx, it->second.d, ctx->ws_scalars.p, n, flags & ~B200ZK_POINTS_BE, ctx->stream, out, it->second.table_c, it->second.n);
+}
+
+template <bool G2>
+int msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t* out) {
+  if (!ctx || !out || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: null argument");
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end() || it->second.g2 != G2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: unknown handle");
+  if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: n exceeds the resident bases");
+  return msm_device<G2>(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, stream, out, it->second.table_c, it->second.n);
+}
+
+template <bool G2>
+int bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) {
+  if (!ctx || !handle || (!d_points && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_from_device: null argument");
+  BasesEntry e;
+  e.n = n; e.g2 = G2;
+  cudaStream_t st = pick_stream(ctx, stream);
+  B2_CUDA(ctx, cudaMalloc(&e.d, n * Sizes<G2>::point + 32));
+  cudaError_t ce = n ? cudaMemcpyAsync(e.d, d_points, n * Sizes<G2>::point, cudaMemcpyDeviceToDevice, st) : cudaSuccess;
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { cudaFree(e.d); return fail(ctx, B200ZK_ERR_CUDA, "bases_from_device copy", ce); }
+  *handle = ctx->next_handle++;
+  ctx->bases[*handle] = e;
+  return B200ZK_OK;
 }
 
 template <bool G2>
@@ -217,6 +243,33 @@ int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, c
 
 int b200zk_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { return bases_upload<false>(ctx, points, n, flags, handle); }
 int b200zk_g2_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { return bases_upload<true>(ctx, points, n, flags, handle); }
+int b200zk_g1_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) { return bases_from_device<false>(ctx, d_points, n, stream, handle); }
+int b200zk_g2_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) { return bases_from_device<true>(ctx, d_points, n, stream, handle); }
+int b200zk_g1_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[64]) { return msm_resident_device<false>(ctx, handle, d_scalars, n, flags, stream, out); }
+int b200zk_g2_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[128]) { return msm_resident_device<true>(ctx, handle, d_scalars, n, flags, stream, out); }
+
+int b200zk_bases_precompute(b200zk_ctx* ctx, uint64_t handle, uint32_t window_bits) {
+  if (!ctx) return B200ZK_ERR_INVALID_ARG;
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end()) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_precompute: unknown handle");
+  if (window_bits && (window_bits < 2 || window_bits > 24)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_precompute: window must be 0 or 2..24");
+  BasesEntry& e = it->second;
+  if (e.table_c) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_precompute: handle already precomputed");
+  const uint32_t c = window_bits ? window_bits : precompute_window(e.n);
+  const uint32_t W = (255 + c - 1) / c;
+  const size_t pt = e.g2 ? 128 : 64;
+  if ((unsigned long long)e.n * W >= (1ull << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "bases_precompute: table exceeds 31-bit indices");
+  void* table = nullptr;
+  B2_CUDA(ctx, cudaMalloc(&table, (size_t)W * e.n * pt + 32));
+  int rc = e.g2 ? msm_precompute_g2(ctx, e.d, e.n, c, table, ctx->stream) : msm_precompute_g1(ctx, e.d, e.n, c, table, ctx->stream);
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+  if (rc > B200ZK_OK_INFINITY || ce != cudaSuccess) { cudaFree(table); return rc > B200ZK_OK_INFINITY ? rc : fail(ctx, B200ZK_ERR_CUDA, "bases_precompute", ce); }
+  cudaFree(e.d);
+  e.d = table;
+  e.table_c = c;
+  return B200ZK_OK;
+}
+
 int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle) {
   if (!ctx) return B200ZK_ERR_INVALID_ARG;
   auto it = ctx->bases.find(handle);
@@ -262,6 +315,20 @@ int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const vo
   if (!ctx || !d_partial256 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial: null argument");
   if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
   return msm_run_g2(ctx, d_points, d_scalars, n, flags, pick_stream(ctx, stream), d_partial256);
+}
+int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) {
+  if (!ctx || !d_partial128 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
+  return msm_run_g1(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n);
+}
+int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
+  if (!ctx || !d_partial256 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end() || !it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
+  return msm_run_g2(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial256, it->second.table_c, it->second.n);
 }
 int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[64]) { return fold_partials<false>(ctx, d_partials, count, flags, stream, out); }
 int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[128]) { return fold_partials<true>(ctx, d_partials, count, flags, stream, out); }

@@ -34,7 +34,7 @@ template <class F> B2_D XYZZ<F> xyzz_mdbl(const F& x1, const F& y1) {
   F xx = F::sqr(x1), M = F::add(F::dbl(xx), xx);
   XYZZ<F> r;
   r.x = F::sub(F::sqr(M), F::dbl(S));
-  r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, y1));
+  r.y = F::mul2_sub(M, F::sub(S, r.x), W, y1);
   r.zz = V; r.zzz = W;
   return r;
 }
@@ -46,7 +46,7 @@ template <class F> B2_D XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
   F xx = F::sqr(p.x), M = F::add(F::dbl(xx), xx);
   XYZZ<F> r;
   r.x = F::sub(F::sqr(M), F::dbl(S));
-  r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+  r.y = F::mul2_sub(M, F::sub(S, r.x), W, p.y);
   r.zz = F::mul(V, p.zz); r.zzz = F::mul(W, p.zzz);
   return r;
 }
@@ -64,7 +64,7 @@ template <class F> B2_D void xyzz_add_mixed(XYZZ<F>& acc, const F& x2, const F& 
   }
   F PP = F::sqr(P), PPP = F::mul(P, PP), Q = F::mul(acc.x, PP);
   F x3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-  acc.y = F::sub(F::mul(R, F::sub(Q, x3)), F::mul(acc.y, PPP));
+  acc.y = F::mul2_sub(R, F::sub(Q, x3), acc.y, PPP);
   acc.x = x3;
   acc.zz = F::mul(acc.zz, PP);
   acc.zzz = F::mul(acc.zzz, PPP);
@@ -84,7 +84,7 @@ template <class F> B2_D void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
   }
   F PP = F::sqr(P), PPP = F::mul(P, PP), Q = F::mul(U1, PP);
   F x3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
-  acc.y = F::sub(F::mul(R, F::sub(Q, x3)), F::mul(S1, PPP));
+  acc.y = F::mul2_sub(R, F::sub(Q, x3), S1, PPP);
   acc.x = x3;
   acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);
   acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);

@@ -232,6 +232,50 @@ struct Fe {
   }
   static B2_D Fe sqr(const Fe& a) { return mul(a, a); }
 
+  // a*b + c*d (Montgomery), ONE reduction for the two products: 24 wide multiply-adds per round instead of
+  // 2 x 16.  Bound: with all inputs < p the running total stays below 2^256 + 2*2^286 + 2^286 < 2^288 (nine
+  // columns, as in mul) and the result is < 2p^2/2^256 + p < 1.4p, so one conditional subtraction finishes it.
+  // The curve formulas use it for Y3 = R*(Q - X3) - Y1*PPP  (c = p - Y1).
+  static B2_D Fe mul2_add(const Fe& a, const Fe& b, const Fe& c, const Fe& d) {
+    uint32_t ev[8], od[8];
+    uint32_t m;
+    detail::mul_even(ev, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+    detail::mul_even(od, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+    detail::mad_odd(od, c.v[1], c.v[3], c.v[5], c.v[7], d.v[0]);
+    detail::mad_even(ev, od[7], c.v[0], c.v[2], c.v[4], c.v[6], d.v[0]);
+    m = ev[0] * Cfg::INV;
+    detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+      detail::shift_mad_odd(ev, od[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+      detail::mad_even(od, ev[7], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+      detail::mad_odd(ev, c.v[1], c.v[3], c.v[5], c.v[7], d.v[i]);
+      detail::mad_even(od, ev[7], c.v[0], c.v[2], c.v[4], c.v[6], d.v[i]);
+      m = od[0] * Cfg::INV;
+      detail::mad_odd(ev, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+      detail::mad_even(od, ev[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+      if (i + 1 < 8) {
+        detail::shift_mad_odd(od, ev[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+        detail::mad_even(ev, od[7], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+        detail::mad_odd(od, c.v[1], c.v[3], c.v[5], c.v[7], d.v[i + 1]);
+        detail::mad_even(ev, od[7], c.v[0], c.v[2], c.v[4], c.v[6], d.v[i + 1]);
+        m = ev[0] * Cfg::INV;
+        detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+        detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+      }
+    }
+    Fe r;
+    asm("add.cc.u32  %0, %8,  %16;\n\t addc.cc.u32 %1, %9,  %17;\n\t addc.cc.u32 %2, %10, %18;\n\t addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t addc.cc.u32 %5, %13, %21;\n\t addc.cc.u32 %6, %14, %22;\n\t addc.u32    %7, %15, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+          "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+    return reduce_once(r);
+  }
+  // a*b - c*d
+  static B2_D Fe mul2_sub(const Fe& a, const Fe& b, const Fe& c, const Fe& d) { return mul2_add(a, b, neg(c), d); }
+
   static B2_D Fe to_mont(const Fe& canonical) { return mul(canonical, rsquared()); }
   static B2_D Fe from_mont(const Fe& a) {
     Fe o = zero(); o.v[0] = 1; return mul(a, o);
@@ -278,6 +322,8 @@ struct Fq2 {
     Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
     return {Fq::mul(s, d), Fq::dbl(m)};
   }
+  // a*b - c*d over Fq2 (no merged form yet: the base-field reductions are already shared inside mul)
+  static B2_D Fq2 mul2_sub(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return sub(mul(a, b), mul(c, d)); }
   static B2_D Fq2 inv(const Fq2& a) {
     Fq d = Fq::inv(Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1)));
     return {Fq::mul(a.c0, d), Fq::neg(Fq::mul(a.c1, d))};

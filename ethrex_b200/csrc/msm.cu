@@ -30,7 +30,21 @@ static constexpr int kChunk = 32;  // buckets per running-sum chunk
 struct MsmPlan {
   uint32_t c, W, B;       // window bits, windows, buckets per window (2^(c-1))
   uint32_t chunk, T;      // buckets per chunk, chunks per window
+  uint32_t merged;        // 1: bases carry precomputed 2^(c*w) multiples, all windows share ONE bucket set
+  uint32_t Wr;            // bucket sets to reduce: W, or 1 when merged
+  uint32_t table_stride;  // merged: bases of window w start at w * table_stride
 };
+
+// window for a precomputed table (all windows share the buckets, so c can be larger: fewer windows)
+uint32_t precompute_window(size_t n) {
+  uint32_t lg = 0;
+  while (((size_t)1 << lg) < n) ++lg;
+  // measured on B200 (profiles/): c = 20 wins at 2^20 and 2^24 (beyond it the scatter's atomics over 2^(c-1)
+  // counters and the bucket reduction cost more than the saved window)
+  if (lg >= 20) return 20;
+  if (lg <= 6) return 6;
+  return lg;
+}
 
 static MsmPlan make_plan(size_t n, uint32_t forced_c) {
   uint32_t lg = 0;
@@ -46,6 +60,7 @@ static MsmPlan make_plan(size_t n, uint32_t forced_c) {
   p.B = 1u << (c - 1);
   p.chunk = p.B < (uint32_t)kChunk ? p.B : (uint32_t)kChunk;
   p.T = p.B / p.chunk;
+  p.merged = 0; p.Wr = p.W; p.table_stride = 0;
   return p;
 }
 
@@ -122,7 +137,7 @@ __global__ void __launch_bounds__(256) msm_hist(const void* scalars, size_t n, u
       digits[(size_t)w * n + i] = code;
       uint32_t rank, gm;
       uint32_t cnt = warp_group(mag - 1, mag != 0, &rank, &gm);
-      if (mag && rank == 0) atomicAdd(&hist[(size_t)w * pl.B + (mag - 1)], cnt);
+      if (mag && rank == 0) atomicAdd(&hist[(pl.merged ? 0 : (size_t)w * pl.B) + (mag - 1)], cnt);
     }
   }
 }
@@ -135,14 +150,15 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
     uint32_t code = t < total ? __ldg(digits + t) : kNoDigit;
     bool active = code != kNoDigit;
     size_t w = t / n;  // a warp may straddle two windows at the seam: key on the global bucket id
-    uint32_t g = (uint32_t)(w * pl.B) + (code & 0x7fffffffu);
+    uint32_t g = (pl.merged ? 0u : (uint32_t)(w * pl.B)) + (code & 0x7fffffffu);
     uint32_t rank, mask;
     uint32_t cnt = warp_group(g, active, &rank, &mask);
     uint32_t base = 0;
     if (active && rank == 0) base = atomicAdd(&cursor[g], cnt);
     // broadcast the leader's base to its group: leader = lowest lane of the group
     base = __shfl_sync(mask, base, __ffs(mask) - 1);
-    if (active) idx[base + rank] = (uint32_t)(t - w * n) | (code & 0x80000000u);
+    // merged: the entry addresses the precomputed multiple 2^(c*w) * P_i directly
+    if (active) idx[base + rank] = (uint32_t)((t - w * n) + (pl.merged ? w * pl.table_stride : 0)) | (code & 0x80000000u);
   }
 }
 
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(128) partial_tree(const uint32_t* __restrict__
 template <class F>
 __global__ void __launch_bounds__(128) bucket_chunk(const void* __restrict__ partials, const uint32_t* __restrict__ seg_off, MsmPlan pl, void* __restrict__ chunkS, void* __restrict__ chunkV) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t total = (size_t)pl.W * pl.T;
+  size_t total = (size_t)pl.Wr * pl.T;
   if (t >= total) return;
   size_t first = t * pl.chunk;  // bucket arrays are [w][b] contiguous and T*chunk == B
   XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
@@ -336,7 +352,7 @@ template <class F>
 __global__ void __launch_bounds__(128) bucket_tree(MsmPlan pl, uint32_t half, uint32_t shift_log2, void* __restrict__ chunkS, void* __restrict__ chunkV) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   uint32_t pairs = pl.T / (2 * half);
-  if (t >= (size_t)pl.W * pairs) return;
+  if (t >= (size_t)pl.Wr * pairs) return;
   size_t w = t / pairs, j = (t % pairs) * 2 * half;
   size_t left = w * pl.T + j, right = left + half;
   XYZZ<F> Sl = load_xyzz<F>(chunkS, left), Sr = load_xyzz<F>(chunkS, right);
@@ -352,8 +368,8 @@ __global__ void __launch_bounds__(128) bucket_tree(MsmPlan pl, uint32_t half, ui
 template <class F>
 __global__ void msm_horner(MsmPlan pl, const void* __restrict__ chunkV, void* __restrict__ result) {
   if (blockIdx.x || threadIdx.x) return;
-  XYZZ<F> acc = load_xyzz<F>(chunkV, (size_t)(pl.W - 1) * pl.T);
-  for (int w = (int)pl.W - 2; w >= 0; --w) {
+  XYZZ<F> acc = load_xyzz<F>(chunkV, (size_t)(pl.Wr - 1) * pl.T);
+  for (int w = (int)pl.Wr - 2; w >= 0; --w) {
     for (uint32_t k = 0; k < pl.c; ++k) acc = xyzz_dbl(acc);
     XYZZ<F> s = load_xyzz<F>(chunkV, (size_t)w * pl.T);
     xyzz_add(acc, s);
@@ -398,15 +414,20 @@ static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
 }
 
 template <class F>
-static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial) {
+static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial,
+                   uint32_t table_c, size_t table_stride) {
   if (n == 0) {
     B2_LAUNCH(ctx, write_identity<F>, 1, 32, 0, st, d_partial);
     return B200ZK_OK;
   }
   if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
-  const MsmPlan pl = make_plan(n, ctx->msm_window);
+  MsmPlan pl = make_plan(n, table_c ? table_c : ctx->msm_window);
+  if (table_c) {
+    pl.merged = 1; pl.Wr = 1; pl.table_stride = (uint32_t)table_stride;
+    if ((unsigned long long)table_stride * pl.W >= (1ull << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: precomputed table too large for 31-bit indices");
+  }
   if ((unsigned long long)n * pl.W >= (1ull << 32)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32 (shard the MSM)");
-  const size_t G = (size_t)pl.W * pl.B;
+  const size_t G = (size_t)pl.Wr * pl.B;
   const size_t tiles = (G + kScanTile - 1) / kScanTile;
   const size_t xy = 4 * FieldBytes<F>::value;
   B2_TRY(ensure(ctx, ctx->ws_hist, G * 4));
@@ -420,8 +441,8 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));     // segment partials (bucket totals after partial_tree)
   B2_TRY(ensure(ctx, ctx->ws_segoff, (G + 1) * 4));
   B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
-  B2_TRY(ensure(ctx, ctx->ws_chunkS, (size_t)pl.W * pl.T * xy));
-  B2_TRY(ensure(ctx, ctx->ws_chunkV, (size_t)pl.W * pl.T * xy));
+  B2_TRY(ensure(ctx, ctx->ws_chunkS, (size_t)pl.Wr * pl.T * xy));
+  B2_TRY(ensure(ctx, ctx->ws_chunkV, (size_t)pl.Wr * pl.T * xy));
   uint32_t* hist = (uint32_t*)ctx->ws_hist.p;
   uint32_t* offsets = (uint32_t*)ctx->ws_offsets.p;
   uint32_t* cursor = (uint32_t*)ctx->ws_cursor.p;
@@ -449,17 +470,17 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((slices + 127) / 128), 128, 0, st, d_points, idx, offsets, seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
   {
     // worst case every point of a window lands in one bucket: ceil(n / kSegLen) + 1 runs to fold
-    size_t worst = (n + kSegLen - 1) / kSegLen + 1;
+    size_t worst = ((pl.merged ? n * (size_t)pl.W : n) + kSegLen - 1) / kSegLen + 1;
     for (size_t stride = 1; stride < worst; stride *= kTreeRadix)
       B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, seg_off, seg_bucket, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
   }
   phase_mark(ctx, 4, st);
-  const size_t chunks = (size_t)pl.W * pl.T;
+  const size_t chunks = (size_t)pl.Wr * pl.T;
   B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, seg_off, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
   uint32_t chunk_log2 = 0;
   while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
   for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
-    size_t pairs = (size_t)pl.W * (pl.T / (2 * half));
+    size_t pairs = (size_t)pl.Wr * (pl.T / (2 * half));
     B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
   }
   phase_mark(ctx, 5, st);
@@ -474,8 +495,32 @@ static int msm_encode_host(b200zk_ctx* ctx, const void* d_partials, size_t count
   return B200ZK_OK;
 }
 
-int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out) { return msm_run<Fq>(ctx, p, s, n, f, st, out); }
-int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out) { return msm_run<Fq2>(ctx, p, s, n, f, st, out); }
+// table[w * n + i] = 2^(c*w) * P_i as an affine point, w = 0..W-1 (window 0 = the bases themselves).
+// One thread per base; one Fermat inversion per (base, window) -- a one-off cost when the proving key is loaded.
+template <class F>
+__global__ void __launch_bounds__(128) precompute_windows(const void* __restrict__ bases, size_t n, uint32_t c, uint32_t W, void* __restrict__ table) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = load_affine_nc<F>(bases, i);
+  store_affine<F>(table, i, p);
+  for (uint32_t w = 1; w < W; ++w) {
+    XYZZ<F> q = xyzz_from_affine(p);
+    for (uint32_t k = 0; k < c; ++k) q = xyzz_dbl(q);
+    p = xyzz_to_affine(q);
+    store_affine<F>(table, (size_t)w * n + i, p);
+  }
+}
+template <class F>
+static int precompute_host(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st) {
+  const uint32_t W = (255 + c - 1) / c;
+  if (n) B2_LAUNCH(ctx, precompute_windows<F>, (unsigned)((n + 127) / 128), 128, 0, st, d_bases, n, c, W, d_table);
+  return B200ZK_OK;
+}
+int msm_precompute_g1(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fq>(ctx, b, n, c, t, st); }
+int msm_precompute_g2(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fq2>(ctx, b, n, c, t, st); }
+
+int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts) { return msm_run<Fq>(ctx, p, s, n, f, st, out, tc, ts); }
+int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts) { return msm_run<Fq2>(ctx, p, s, n, f, st, out, tc, ts); }
 int msm_encode_g1(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq>(ctx, p, c, f, st, out); }
 int msm_encode_g2(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq2>(ctx, p, c, f, st, out); }
 

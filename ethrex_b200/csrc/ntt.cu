@@ -11,8 +11,9 @@
 //     V     = NTT_R(v)                                                     (s_p radix-2 stages in shared memory)
 //     out[(j div Ns)*Ns*R + (j mod Ns) + q*Ns] = V[q]
 // One CTA owns a tile of 2^t adjacent j, so every global access is a run of 2^t * 32 B, and the R-point
-// transforms of a tile never leave shared memory.  Inter-pass twiddles come from two 4096-entry tables
-// (w^lo, w^(hi*4096)): one extra multiplication instead of an n/2-entry table streamed from HBM.
+// transforms of a tile never leave shared memory.  Inter-pass twiddles come from one 2^16-entry table when
+// Ns*R <= 2^16 (a single lookup), else from two 4096-entry tables (w^lo, w^(hi*4096)): one extra
+// multiplication instead of an n/2-entry table streamed from HBM.
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -28,7 +29,9 @@ struct NttTables {
   const uint4* lo;     // lo[x] = w_N^x, x < 2^min(12, k)
   const uint4* hi;     // hi[y] = w_N^(y << 12)
   const uint4* ninv;   // n^-1
+  const uint4* d16;    // d16[x] = w_{2^16}^x, x < 2^16: inter-pass twiddles of passes with Ns*R <= 2^16 in ONE lookup
 };
+static constexpr uint32_t kDirectBits = 16;
 
 B2_D Fr fr_root_2_28() {  // 5^((r-1)/2^28), canonical 0x2a3c09f0a58a7e85...725b19f0
   const uint32_t g[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
@@ -48,13 +51,19 @@ B2_D Fr root_of_unity(uint32_t log_n) {
   return w;
 }
 
-// entries: [0, 4095) stage tables, then 2^lb lo, then 2^(k-lb) hi, then n^-1
+// entries: [0, 4095) stage tables, then 2^lb lo, then 2^(k-lb) hi, then n^-1, then 2^16 direct
 __global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inverse, void* out, uint32_t n_lo, uint32_t n_hi) {
   uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_stage = (1u << kMaxStage) - 1;
   uint32_t total = n_stage + n_lo + n_hi + 1;
-  if (id >= total) return;
+  if (id >= total + (1u << kDirectBits)) return;
   Fr val;
+  if (id >= total) {
+    uint32_t x = id - total, D = 1u << kDirectBits;
+    val = fr_pow_u32(root_of_unity(kDirectBits), inverse ? (D - x) & (D - 1) : x);
+    store_fe<Fr>(out, id, val);
+    return;
+  }
   if (id < n_stage) {
     uint32_t s = 32 - __clz(id + 1);           // id+1 in [2^(s-1), 2^s)
     uint32_t i = id + 1 - (1u << (s - 1));
@@ -109,10 +118,15 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
     uint32_t j = j0 + c;
     Fr v = load_fe<Fr>(a.in, (size_t)j + ((size_t)r << stride_log));
     if (lns) {
-      uint32_t e = (r * (j & ns_mask)) << (k - lns - s);
-      Fr tw = load_fe_nc<Fr>(a.tb.lo, e & ((1u << kLoBits) - 1));
-      if (k > (uint32_t)kLoBits) tw = Fr::mul(tw, load_fe_nc<Fr>(a.tb.hi, e >> kLoBits));
-      v = Fr::mul(v, tw);
+      const uint32_t x = r * (j & ns_mask), L = lns + s;  // twiddle = w_{2^L}^x
+      Fr tw;
+      if (L <= kDirectBits) {
+        tw = load_fe_nc<Fr>(a.tb.d16, x << (kDirectBits - L));
+      } else {
+        uint32_t e = x << (k - L);
+        tw = Fr::mul(load_fe_nc<Fr>(a.tb.lo, e & ((1u << kLoBits) - 1)), load_fe_nc<Fr>(a.tb.hi, e >> kLoBits));
+      }
+      if (x) v = Fr::mul(v, tw);
     }
     sts_fr(sm, it, v);  // sm[(r << t) + c]
   }
@@ -123,14 +137,20 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
   const uint32_t half_items = items >> 1;
   for (uint32_t q = 0; q < s; ++q) {
     const uint32_t lm = s - 1 - q, m = 1u << lm;
+    // Butterfly u of this stage = (block, jj) with twiddle w_{2m}^jj.  Where possible jj is taken from the HIGH
+    // bits of u, so that the lanes of a warp share one jj: the twiddle load is a broadcast and the jj == 0
+    // butterflies (twiddle 1: half of them at m = 2, a quarter at m = 4, ...) skip the product warp-uniformly.
+    const bool uniform = lm + 3 <= s;
+    const uint32_t hb = s - 1 - lm;
     for (uint32_t it = threadIdx.x; it < half_items; it += THREADS) {
-      uint32_t c = it & cmask, bf = it >> t;
-      uint32_t jj = bf & (m - 1);
-      uint32_t i = ((bf >> lm) << (lm + 1)) | jj;
+      uint32_t c = it & cmask, u = it >> t;
+      uint32_t jj = uniform ? (u >> hb) : (u & (m - 1));
+      uint32_t blk = uniform ? (u & ((1u << hb) - 1)) : (u >> lm);
+      uint32_t i = (blk << (lm + 1)) | jj;
       uint32_t p0 = (i << t) + c, p1 = ((i + m) << t) + c;
       Fr x = lds_fr(sm, p0), y = lds_fr(sm, p1);
       Fr d = Fr::sub(x, y);
-      if (m > 1) d = Fr::mul(d, load_fe_nc<Fr>(stage_tw, jj << q));
+      if (jj) d = Fr::mul(d, load_fe_nc<Fr>(stage_tw, jj << q));
       sts_fr(sm, p0, Fr::add(x, y));
       sts_fr(sm, p1, d);
     }
@@ -212,9 +232,9 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
   auto it = ctx->twiddles.find(key);
   if (it == ctx->twiddles.end()) {
     TwiddleSet ts;
-    ts.bytes = (size_t)(n_stage + n_lo + n_hi + 1) * 32;
+    ts.bytes = (size_t)(n_stage + n_lo + n_hi + 1 + (1u << kDirectBits)) * 32;
     B2_CUDA(ctx, cudaMalloc(&ts.d, ts.bytes));
-    uint32_t total = n_stage + n_lo + n_hi + 1;
+    uint32_t total = n_stage + n_lo + n_hi + 1 + (1u << kDirectBits);
     B2_LAUNCH(ctx, ntt_build_tables, (total + 127) / 128, 128, 0, st, log_n, inverse ? 1 : 0, ts.d, n_lo, n_hi);
     it = ctx->twiddles.emplace(key, ts).first;
   }
@@ -223,6 +243,7 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
   out->lo = base + 2 * (size_t)n_stage;
   out->hi = out->lo + 2 * (size_t)n_lo;
   out->ninv = out->hi + 2 * (size_t)n_hi;
+  out->d16 = out->ninv + 2;
   return B200ZK_OK;
 }
 

@@ -18,14 +18,18 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def msm_sharded(ctx, d_points, d_scalars, n_local: int, flags: int = 0, g2: bool = False, group=None) -> bytes:
-    """MSM over the union of all ranks' shards.  `d_points`/`d_scalars`: this rank's shard (device tensors)."""
+def msm_sharded(ctx, d_points, d_scalars, n_local: int, flags: int = 0, g2: bool = False, group=None, handle: int | None = None) -> bytes:
+    """MSM over the union of all ranks' shards.  `d_points`/`d_scalars`: this rank's shard (device tensors);
+    with `handle` the shard's bases are the resident (possibly precomputed) ones and `d_points` is ignored."""
     import torch
     import torch.distributed as dist
     words = 32 if g2 else 16  # XYZZ partial in int64 words
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     partial = torch.zeros(words, dtype=torch.int64, device=d_scalars.device)
-    (ctx.g2_msm_partial_device if g2 else ctx.g1_msm_partial_device)(d_points, d_scalars, n_local, partial, flags)
+    if handle is not None:
+        (ctx.g2_msm_partial_resident_device if g2 else ctx.g1_msm_partial_resident_device)(handle, d_scalars, n_local, partial, flags)
+    else:
+        (ctx.g2_msm_partial_device if g2 else ctx.g1_msm_partial_device)(d_points, d_scalars, n_local, partial, flags)
     if world == 1:
         gathered = partial
     else:

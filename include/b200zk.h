@@ -100,12 +100,25 @@ int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, c
 /* ---- resident bases: the proving key (SRS) lives in HBM across proofs ---------------------------------- */
 int b200zk_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle);
 int b200zk_g2_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle);
+/* same, from points already in device memory (native format); the library keeps its own copy */
+int b200zk_g1_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle);
+int b200zk_g2_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle);
+/* One-off, when the proving key is loaded: replace the resident bases by a table of their window multiples
+ * 2^(c*w) * P_i, w = 0..ceil(255/c)-1 (W times the memory).  All windows then share ONE bucket set: larger
+ * windows pay off (c = 22 -> 12 n additions instead of 15 n at 2^24) and the final Horner pass disappears.
+ * window_bits = 0 picks c from n.  Results are unchanged (same group element). */
+int b200zk_bases_precompute(b200zk_ctx* ctx, uint64_t handle, uint32_t window_bits);
 int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle);
 /* MSM of the first n resident bases against host scalars */
 int b200zk_g1_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
                            uint8_t out[64]);
 int b200zk_g2_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
                            uint8_t out[128]);
+/* resident bases against scalars already in device memory (`stream` as for the *_device calls below) */
+int b200zk_g1_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n,
+                                  uint32_t flags, void* stream, uint8_t out[64]);
+int b200zk_g2_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n,
+                                  uint32_t flags, void* stream, uint8_t out[128]);
 
 /* ---- device-pointer entry points: inputs already in HBM (native formats only) ------------------------- */
 /* `stream`: a cudaStream_t passed as void*; NULL = the context's own (non-blocking) stream, so pass
@@ -132,6 +145,11 @@ int b200zk_g1_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const vo
                                  uint32_t flags, void* stream, void* d_partial128);
 int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
                                  uint32_t flags, void* stream, void* d_partial256);
+/* same, over resident (possibly precomputed) bases */
+int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n,
+                                          uint32_t flags, void* stream, void* d_partial128);
+int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n,
+                                          uint32_t flags, void* stream, void* d_partial256);
 int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags,
                                    void* stream, uint8_t out[64]);
 int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags,

@@ -370,3 +370,52 @@ def test_launch_counter_moves(ctx):
     d = dev_empty(4 * 16)
     ctx.fr_random_device(d, 16, 1, 0)
     assert ctx.launch_count == before + 1
+
+
+def test_precomputed_window_tables(ctx):
+    """resident bases expanded to 2^(c*w)*P_i: same group element, for full and partial use of the table."""
+    k, d = chain_kd()
+    n = 3000
+    pts = orc.g1_chain(n, k, d)
+    for c in (0, 5, 9, 13):
+        h = ctx.g1_bases_upload(pts, n)
+        ctx.bases_precompute(h, c)
+        try:
+            for m in (n, 777, 1):
+                s = scalars_special(m, seed=400 + m)
+                exp = orc.g1_msm(pts[:m], s)
+                assert ctx.g1_msm_resident(h, s, m) == exp, (c, m)
+                assert ctx.g1_msm_resident_device(h, to_dev(s), m) == exp, (c, m)
+            with pytest.raises(eb.B200Error):
+                ctx.bases_precompute(h, 0)  # already a table
+        finally:
+            ctx.bases_free(h)
+    # from device memory, G2, and edge distributions
+    dp = to_dev(pts)
+    h = ctx.g1_bases_from_device(dp, n)
+    ctx.bases_precompute(h, 11)
+    for vals in ([0] * n, [1] * n, [pyref.R - 1] * n, [(1 << 256) - 1 - i for i in range(n)]):
+        s = orc.ints_to_array(vals)
+        assert ctx.g1_msm_resident_device(h, to_dev(s), n) == orc.g1_msm(pts, s)
+    ctx.bases_free(h)
+    pts2 = orc.g2_chain(600, k, d)
+    h2 = ctx.g2_bases_from_device(to_dev(pts2), 600)
+    ctx.bases_precompute(h2, 0)
+    s = scalars_special(600, seed=9)
+    assert ctx.g2_msm_resident_device(h2, to_dev(s), 600) == orc.g2_msm(pts2, s)
+    assert ctx.g2_msm_resident(h2, s[:100], 100) == orc.g2_msm(pts2[:100], s[:100])
+    ctx.bases_free(h2)
+
+
+def test_precomputed_2_20_closed_form(ctx):
+    n = 1 << 20
+    k, d = chain_kd()
+    dp, ds = dev_empty(8 * n), dev_empty(4 * n)
+    ctx.g1_chain_device(dp, 0, n, k, d)
+    ctx.fr_random_device(ds, n, pyref.SEED_SCALARS, 0)
+    h = ctx.g1_bases_from_device(dp, n)
+    ctx.bases_precompute(h, 0)
+    try:
+        assert ctx.g1_msm_resident_device(h, ds, n) == expected_chain_msm_g1(to_host(ds).reshape(n, 4), k, d)
+    finally:
+        ctx.bases_free(h)
