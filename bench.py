@@ -32,6 +32,18 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) also write to fd 1,
+# so keep a private handle on the real stdout for the result line and point fd 1 at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit_result(line: dict):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 SEED_SCALARS, SEED_POINTS, SEED_NTT = 0xB2000001, 0xB2000002, 0xB2000003
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 
@@ -142,7 +154,7 @@ def run_reference(args):
         "ntt": {"metric": "fr_ntt_elems_per_sec", "value": ntt_rate, "unit": "elements/s", "sample": f"2^{min(22, args.log_n)} forward, {ntt_dt:.3f} s"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -252,26 +264,31 @@ def run_gpu(args):
     if not args.no_e2e:
         h_scalars = torch.empty(4 * n, dtype=torch.int64).pin_memory()
         h_scalars.copy_(d_scalars)
+        d_stage = torch.empty(4 * n, dtype=torch.int64, device="cuda") if world > 1 else None
+
         def e2e_step():
             if world == 1:
                 result["e2e"] = ctx.g1_msm_resident(handle, h_scalars, n)
-            else:
-                raise NotImplementedError
-        if world == 1:
-            for _ in range(max(1, args.warmup // 2)):
-                e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                e2e_step()
-            e1.record()
-            barrier()
-            wall = (time.perf_counter() - t0) / args.steps
-            assert result["e2e"] == result["out"]
-            e2e = {"value": n / wall, "unit": "points/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 64,
-                   "ms_per_step": wall * 1e3, "api": "b200zk_g1_msm_resident (pinned host scalars, bases resident in HBM)"}
+            else:  # every rank ships its own shard of scalars, then partial -> all_gather -> fold
+                d_stage.copy_(h_scalars, non_blocking=True)
+                result["e2e"] = msm_sharded(ctx, None, d_stage, n, handle=handle)
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        wall_t = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
+        wall = float(wall_t.item())
+        assert result["e2e"] == result["out"]
+        e2e = {"value": world * n / wall, "unit": "points/s", "h2d_bytes_per_step": world * n * 32, "d2h_bytes_per_step": world * 64,
+               "ms_per_step": wall * 1e3,
+               "api": "b200zk_g1_msm_resident (pinned host scalars -> result bytes; bases resident in HBM)" if world == 1 else
+                      "pinned host scalars -> H2D -> ethrex_b200.dist.msm_sharded (partial, NCCL all_gather, fold) -> result bytes"}
+        del d_stage
         del h_scalars
 
     # ---- NTT half of the metric: forward + inverse at 2^log_n, resident, K steps each
@@ -319,7 +336,7 @@ def run_gpu(args):
                        "multi_gpu": "point-split, NCCL all_gather of 128-B XYZZ partials + local fold" if world > 1 else "single GPU"},
             "verified_vs_oracle": verified, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "ntt": ntt, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -332,7 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
-    ap.add_argument("--cpu-log-n", type=int, default=21, help="size of the CPU-arm sample (2^k points)")
+    ap.add_argument("--cpu-log-n", type=int, default=22, help="size of the CPU-arm sample (2^k points)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -96,6 +96,9 @@ class Context:
     def set_msm_window(self, c: int):
         self._check(F.lib.b200zk_set_msm_window(self._h, c), "set_msm_window")
 
+    def set_msm_pair_rounds(self, rounds: int):
+        self._check(F.lib.b200zk_set_msm_pair_rounds(self._h, rounds), "set_msm_pair_rounds")
+
     def set_profiling(self, on: bool):
         self._check(F.lib.b200zk_set_profiling(self._h, 1 if on else 0), "set_profiling")
 

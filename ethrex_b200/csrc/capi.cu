@@ -190,7 +190,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   DevBuf* bufs[] = {&ctx->ws_hist, &ctx->ws_offsets, &ctx->ws_cursor, &ctx->ws_blocksums, &ctx->ws_idx, &ctx->ws_buckets, &ctx->ws_chunkS,
-                    &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits};
+                    &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits, &ctx->ws_q0, &ctx->ws_q1, &ctx->ws_prefix, &ctx->ws_info, &ctx->ws_pairoff0, &ctx->ws_pairoff1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   for (auto& kv : ctx->twiddles) cudaFree(kv.second.d);
   for (auto& kv : ctx->bases) cudaFree(kv.second.d);
@@ -210,6 +210,11 @@ int b200zk_synchronize(b200zk_ctx* ctx) {
 int b200zk_set_msm_window(b200zk_ctx* ctx, uint32_t c) {
   if (!ctx || (c && (c < 2 || c > 24))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm window must be 0 or 2..24");
   ctx->msm_window = c;
+  return B200ZK_OK;
+}
+int b200zk_set_msm_pair_rounds(b200zk_ctx* ctx, int rounds) {
+  if (!ctx || rounds > 4) return fail(ctx, B200ZK_ERR_INVALID_ARG, "pair rounds must be <= 4 (negative = automatic)");
+  ctx->msm_pair_rounds = rounds < 0 ? -1 : rounds;
   return B200ZK_OK;
 }
 int b200zk_set_profiling(b200zk_ctx* ctx, int enabled) {

@@ -38,12 +38,13 @@ struct b200zk_ctx {
   std::string last_error;
   uint64_t launches = 0;
   uint32_t msm_window = 0;
+  int msm_pair_rounds = -1;  // batched-affine pair-summing rounds before the XYZZ accumulation; <0 = automatic
   bool profiling = false;
   float phase_ms[6] = {0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8] = {};
   // grow-only workspaces
   b200zk::DevBuf ws_hist, ws_offsets, ws_cursor, ws_blocksums, ws_idx, ws_buckets, ws_chunkS, ws_chunkV, ws_result,
-      ws_points, ws_scalars, ws_ntt, ws_misc, ws_out, ws_segoff, ws_segbucket, ws_digits;
+      ws_points, ws_scalars, ws_ntt, ws_misc, ws_out, ws_segoff, ws_segbucket, ws_digits, ws_q0, ws_q1, ws_prefix, ws_info, ws_pairoff0, ws_pairoff1;
   std::map<uint64_t, b200zk::TwiddleSet> twiddles;
   std::map<uint64_t, b200zk::BasesEntry> bases;
   uint64_t next_handle = 1;

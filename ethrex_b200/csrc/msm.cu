@@ -21,6 +21,7 @@
 // The affine normalisation / byte encoding (msm_encode) is a separate single-thread kernel so that the
 // multi-GPU path can all-gather the 128/256-byte XYZZ partials first.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200zk {
 
@@ -65,9 +66,8 @@ static MsmPlan make_plan(size_t n, uint32_t forced_c) {
 }
 
 // ---- scalar loading and signed-digit recoding -----------------------------------------------------------
-B2_D void load_scalar(const void* scalars, size_t i, uint32_t flags, uint32_t s[8]) {
-  const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * i;
-  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+// decode one 32-byte scalar (given as two 128-bit words) into canonical little-endian limbs < r
+B2_D void decode_scalar(uint4 lo, uint4 hi, uint32_t flags, uint32_t s[8]) {
   if (flags & B200ZK_SCALARS_BE) {
     s[7] = __byte_perm(lo.x, 0, 0x0123); s[6] = __byte_perm(lo.y, 0, 0x0123); s[5] = __byte_perm(lo.z, 0, 0x0123); s[4] = __byte_perm(lo.w, 0, 0x0123);
     s[3] = __byte_perm(hi.x, 0, 0x0123); s[2] = __byte_perm(hi.y, 0, 0x0123); s[1] = __byte_perm(hi.z, 0, 0x0123); s[0] = __byte_perm(hi.w, 0, 0x0123);
@@ -123,10 +123,31 @@ B2_D uint32_t warp_group(uint32_t key, bool active, uint32_t* rank, uint32_t* gr
   return __popc(mask);
 }
 
-__global__ void __launch_bounds__(256) msm_hist(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* hist, uint32_t* digits) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    uint32_t s[8];
-    load_scalar(scalars, i, flags, s);
+// Scalars are streamed through shared memory by the copy engine: each CTA walks tiles of 256 scalars (8 KiB),
+// double buffered -- while the warps recode tile k, the bulk copy of tile k+1 is already in flight.
+static constexpr uint32_t kHistTile = 256;
+__global__ void __launch_bounds__(kHistTile) msm_hist(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, uint32_t* hist, uint32_t* digits) {
+  __shared__ __align__(128) uint4 tile[2][kHistTile * 2];
+  __shared__ uint64_t bar[2];
+  const size_t tiles = (n + kHistTile - 1) / kHistTile;
+  if (threadIdx.x == 0) { tma::barrier_init(&bar[0], 1); tma::barrier_init(&bar[1], 1); tma::barrier_init_fence(); }
+  __syncthreads();
+  auto issue = [&](size_t tl, uint32_t buf) {
+    size_t first = tl * kHistTile;
+    uint32_t bytes = (uint32_t)((n - first < kHistTile ? n - first : kHistTile) * 32);
+    tma::barrier_expect(&bar[buf], bytes);
+    tma::bulk_load(tile[buf], reinterpret_cast<const uint8_t*>(scalars) + first * 32, bytes, &bar[buf]);
+  };
+  if (threadIdx.x == 0 && blockIdx.x < tiles) issue(blockIdx.x, 0);
+  uint32_t it = 0;
+  for (size_t tl = blockIdx.x; tl < tiles; tl += gridDim.x, ++it) {
+    const uint32_t buf = it & 1;
+    if (threadIdx.x == 0 && tl + gridDim.x < tiles) issue(tl + gridDim.x, buf ^ 1);  // prefetch the next tile
+    tma::barrier_wait(&bar[buf], (it >> 1) & 1);
+    const size_t i = tl * kHistTile + threadIdx.x;
+    const bool live = i < n;
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) decode_scalar(tile[buf][2 * threadIdx.x], tile[buf][2 * threadIdx.x + 1], flags, s);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < pl.W; ++w) {
       uint32_t coef = window_bits(s, w, pl.c) + carry;
@@ -134,11 +155,12 @@ __global__ void __launch_bounds__(256) msm_hist(const void* scalars, size_t n, u
       uint32_t neg = 0, mag = coef;
       if (w + 1 < pl.W && coef >= pl.B) { carry = 1; neg = 0x80000000u; mag = (1u << pl.c) - coef; }  // ark make_digits rule
       uint32_t code = mag ? ((mag - 1) | neg) : kNoDigit;
-      digits[(size_t)w * n + i] = code;
+      if (live) digits[(size_t)w * n + i] = code;
       uint32_t rank, gm;
-      uint32_t cnt = warp_group(mag - 1, mag != 0, &rank, &gm);
-      if (mag && rank == 0) atomicAdd(&hist[(pl.merged ? 0 : (size_t)w * pl.B) + (mag - 1)], cnt);
+      uint32_t cnt = warp_group(mag - 1, live && mag != 0, &rank, &gm);
+      if (live && mag && rank == 0) atomicAdd(&hist[(pl.merged ? 0 : (size_t)w * pl.B) + (mag - 1)], cnt);
     }
+    __syncthreads();  // everyone is done with tile[buf] before it is refilled two iterations later
   }
 }
 
@@ -169,18 +191,19 @@ static constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThread
 // seg  > 0: scan the flag "bucket i is non-empty and does not start on a multiple of seg" (aux = bucket offsets);
 //           scan_apply then adds ceil(offset/seg), giving run_off[i] = index of the first RUN of bucket i when the
 //           sorted entries are cut at every multiple of seg and at every bucket start (see msm_accumulate).
-B2_D uint32_t scan_value(const uint32_t* in, const uint32_t* aux, size_t i, uint32_t seg) {
+// shift: the counts scanned are ceil(in[i] / 2^shift) -- bucket sizes after `shift` rounds of pair-summing.
+B2_D uint32_t scan_value(const uint32_t* in, const uint32_t* aux, size_t i, uint32_t seg, uint32_t shift) {
   uint32_t v = in[i];
-  if (!seg) return v;
+  if (!seg) return (v + (1u << shift) - 1u) >> shift;
   return (v != 0 && (aux[i] % seg) != 0) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, const uint32_t* aux, size_t G, uint32_t seg, uint32_t* tile_sums) {
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* in, const uint32_t* aux, size_t G, uint32_t seg, uint32_t shift, uint32_t* tile_sums) {
   __shared__ uint32_t red[kScanThreads / 32];
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += scan_value(in, aux, base + k, seg);
+  for (int k = 0; k < kScanItems; ++k) if (base + k < G) s += scan_value(in, aux, base + k, seg, shift);
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -215,12 +238,12 @@ __global__ void __launch_bounds__(1024) scan_tile_offsets(uint32_t* tile_sums, s
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, const uint32_t* aux, size_t G, uint32_t seg, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, const uint32_t* aux, size_t G, uint32_t seg, uint32_t shift, const uint32_t* tile_offsets, uint32_t* offsets, uint32_t* cursor) {
   __shared__ uint32_t warp_tot[kScanThreads / 32];
   size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems], s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? scan_value(in, aux, base + k, seg) : 0; s += v[k]; }
+  for (int k = 0; k < kScanItems; ++k) { v[k] = base + k < G ? scan_value(in, aux, base + k, seg, shift) : 0; s += v[k]; }
   uint32_t incl = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += t; }
@@ -265,7 +288,9 @@ B2_D uint32_t bucket_of(const uint32_t* __restrict__ offsets, uint32_t G, uint32
   return lo;
 }
 
-template <class F>
+// DIRECT: `points` is already the sorted, sign-applied entry array (output of pair_sum); else entries are
+// idx[e] = base index | sign << 31 into the bases / window table.
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
                                                       const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ run_off,
                                                       uint32_t G, void* __restrict__ partials, uint32_t* __restrict__ run_bucket) {
@@ -286,12 +311,12 @@ __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ p
   uint32_t slot = t + (__ldg(run_off + g) - (off0 + kSegLen - 1) / kSegLen) + ((off0 % kSegLen) ? 1u : 0u);
   uint32_t next = __ldg(offsets + g + 1);  // first entry of the following bucket (> e0)
   XYZZ<F> acc = XYZZ<F>::identity();
-  uint32_t v = __ldg(idx + e0);
+  uint32_t v = DIRECT ? e0 : __ldg(idx + e0);
   Affine<F> p = load_affine_nc<F>(points, v & 0x7fffffffu);
   for (uint32_t e = e0; e < e1; ++e) {
     // software prefetch: issue the next gather before the ~1500-instruction addition
     uint32_t vn = v; Affine<F> pn = p;
-    if (e + 1 < e1) { vn = __ldg(idx + e + 1); pn = load_affine_nc<F>(points, vn & 0x7fffffffu); }
+    if (e + 1 < e1) { vn = DIRECT ? e + 1 : __ldg(idx + e + 1); pn = load_affine_nc<F>(points, vn & 0x7fffffffu); }
     if (e == next) {  // bucket boundary: close the run
       store_xyzz(partials, slot, acc);
       run_bucket[slot] = g;
@@ -300,12 +325,106 @@ __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ p
       g = bucket_of(offsets, G, g + 1, e);
       next = __ldg(offsets + g + 1);
     }
-    if (v >> 31) p.y = F::neg(p.y);
+    if (!DIRECT && (v >> 31)) p.y = F::neg(p.y);
     xyzz_add_mixed(acc, p.x, p.y);
     v = vn; p = pn;
   }
   store_xyzz(partials, slot, acc);
   run_bucket[slot] = g;
+}
+
+// ---- batched-affine pair summing ---------------------------------------------------------------------------
+// One round halves every bucket: entries (2k, 2k+1) of a bucket are replaced by their AFFINE sum, an odd last
+// entry is carried over.  An affine addition needs 1/(x2 - x1); a thread owns kPairBatch consecutive outputs and
+// inverts all its denominators with ONE field inversion (Montgomery's trick): forward sweep stores the prefix
+// products, backward sweep peels the inverses off.  Cost per pair: 1 (prefix) + 2 (peel) + 3 (lambda, lambda^2,
+// y3) products + 1/kPairBatch of an inversion  ~ 6.7 products, against 10 for an XYZZ mixed addition; after r
+// rounds the XYZZ accumulation only sees M/2^r entries.  Exceptional pairs (equal points -> tangent, opposite
+// points -> identity, identity operands) put 1 (or 2y) in the batch and are resolved in the backward sweep.
+static constexpr uint32_t kPairBatch = 512;
+
+template <class F, bool INDIRECT>
+B2_D Affine<F> pair_load(const void* __restrict__ points, const uint32_t* __restrict__ idx, uint32_t e) {
+  if (INDIRECT) {
+    uint32_t v = __ldg(idx + e);
+    Affine<F> p = load_affine_nc<F>(points, v & 0x7fffffffu);
+    if (v >> 31) p.y = F::neg(p.y);
+    return p;
+  }
+  return load_affine_nc<F>(points, e);
+}
+// denominator of the pair (a, b); kind: 0 = chord, 1 = tangent, 2 = result is `a`, 3 = result is `b`, 4 = identity
+template <class F> B2_D F pair_denominator(const Affine<F>& a, const Affine<F>& b, int* kind) {
+  if (b.is_inf()) { *kind = 2; return F::one(); }
+  if (a.is_inf()) { *kind = 3; return F::one(); }
+  F dx = F::sub(b.x, a.x);
+  if (!dx.is_zero()) { *kind = 0; return dx; }
+  if (a.y == b.y && !a.y.is_zero()) { *kind = 1; return F::dbl(a.y); }
+  *kind = 4; return F::one();
+}
+
+template <class F, bool INDIRECT>
+__global__ void __launch_bounds__(128) pair_sum(const void* __restrict__ points, const uint32_t* __restrict__ idx,
+                                                const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t G,
+                                                void* __restrict__ prefix, uint32_t* __restrict__ info, void* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t Mout = __ldg(off_out + G);
+  const uint64_t o0_64 = (uint64_t)t * kPairBatch;
+  if (o0_64 >= Mout) return;
+  const uint32_t o0 = (uint32_t)o0_64;
+  const uint32_t o1 = (Mout - o0 > kPairBatch) ? o0 + kPairBatch : Mout;
+  uint32_t g;
+  {
+    uint32_t lo = 0, hi = G;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(off_out + mid) <= o0) lo = mid; else hi = mid; }
+    g = lo;
+  }
+  uint32_t next = __ldg(off_out + g + 1);
+  uint32_t base_out = __ldg(off_out + g), base_in = __ldg(off_in + g), end_in = __ldg(off_in + g + 1);
+  // forward sweep: prefix products of the denominators
+  F prod = F::one();
+  for (uint32_t o = o0; o < o1; ++o) {
+    if (o == next) {
+      g = bucket_of(off_out, G, g + 1, o);
+      next = __ldg(off_out + g + 1);
+      base_out = __ldg(off_out + g); base_in = __ldg(off_in + g); end_in = __ldg(off_in + g + 1);
+    }
+    const uint32_t ea = base_in + 2 * (o - base_out);
+    const bool has_pair = ea + 1 < end_in;
+    info[o] = ea | (has_pair ? 0x80000000u : 0u);
+    store_field(prefix, o, prod);
+    if (has_pair) {
+      Affine<F> a = pair_load<F, INDIRECT>(points, idx, ea), b = pair_load<F, INDIRECT>(points, idx, ea + 1);
+      int kind;
+      F d = pair_denominator(a, b, &kind);
+      if (kind <= 1) prod = F::mul(prod, d);
+    }
+  }
+  F inv = F::inv(prod);
+  // backward sweep
+  for (uint32_t o = o1; o-- > o0;) {
+    const uint32_t w = info[o];
+    const uint32_t ea = w & 0x7fffffffu;
+    Affine<F> a = pair_load<F, INDIRECT>(points, idx, ea);
+    if (!(w >> 31)) { store_affine<F>(out, o, a); continue; }
+    Affine<F> b = pair_load<F, INDIRECT>(points, idx, ea + 1);
+    int kind;
+    F d = pair_denominator(a, b, &kind);
+    Affine<F> r;
+    if (kind <= 1) {
+      F dinv = F::mul(inv, load_field(prefix, o, (const F*)nullptr));  // 1/d
+      inv = F::mul(inv, d);
+      F num;
+      if (kind == 0) num = F::sub(b.y, a.y);
+      else { F xx = F::sqr(a.x); num = F::add(F::dbl(xx), xx); }
+      F lam = F::mul(num, dinv);
+      r.x = F::sub(F::sub(F::sqr(lam), a.x), b.x);
+      r.y = F::sub(F::mul(lam, F::sub(a.x, r.x)), a.y);
+    } else if (kind == 2) r = a;
+    else if (kind == 3) r = b;
+    else r = {F::zero(), F::zero()};
+    store_affine<F>(out, o, r);
+  }
 }
 
 template <class F>
@@ -436,8 +555,24 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_TRY(ensure(ctx, ctx->ws_blocksums, tiles * 4));
   B2_TRY(ensure(ctx, ctx->ws_idx, n * (size_t)pl.W * 4));
   B2_TRY(ensure(ctx, ctx->ws_digits, n * (size_t)pl.W * 4));
-  const size_t S_max = (n * (size_t)pl.W) / kSegLen + 1 + G;  // upper bound on the number of runs
-  const size_t slices = (n * (size_t)pl.W + kSegLen - 1) / kSegLen;
+  const size_t M_max = n * (size_t)pl.W;
+  // pair-summing rounds (auto: worth it once buckets hold a few dozen entries on average)
+  uint32_t rounds = 0;
+  if (ctx->msm_pair_rounds >= 0) rounds = (uint32_t)ctx->msm_pair_rounds;
+  else { size_t avg = M_max / G; rounds = avg >= 96 ? 2 : (avg >= 24 ? 1 : 0); }
+  if (rounds > 4) rounds = 4;
+  if (rounds && M_max >= ((size_t)1 << 31)) rounds = 0;
+  const size_t S_max = (M_max >> rounds) / kSegLen + 1 + G;  // upper bound on the number of runs
+  const size_t slices = ((M_max >> rounds) + G + kSegLen - 1) / kSegLen;
+  if (rounds) {
+    const size_t pt = 2 * FieldBytes<F>::value;
+    B2_TRY(ensure(ctx, ctx->ws_q1, (M_max / 2 + G + 1) * pt));
+    if (rounds > 1) B2_TRY(ensure(ctx, ctx->ws_q0, (M_max / 4 + G + 1) * pt));
+    B2_TRY(ensure(ctx, ctx->ws_prefix, (M_max / 2 + G + 1) * FieldBytes<F>::value));
+    B2_TRY(ensure(ctx, ctx->ws_info, (M_max / 2 + G + 1) * 4));
+    B2_TRY(ensure(ctx, ctx->ws_pairoff0, (G + 1) * 4));
+    B2_TRY(ensure(ctx, ctx->ws_pairoff1, (G + 1) * 4));
+  }
   B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));     // segment partials (bucket totals after partial_tree)
   B2_TRY(ensure(ctx, ctx->ws_segoff, (G + 1) * 4));
   B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
@@ -451,26 +586,44 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
 
   phase_mark(ctx, 0, st);
   B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
-  const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+  const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
   uint32_t* digits = (uint32_t*)ctx->ws_digits.p;
   B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist, digits);
   phase_mark(ctx, 1, st);
-  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, tsum);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
-  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, tsum, offsets, cursor);
-  uint32_t* seg_off = (uint32_t*)ctx->ws_segoff.p;
-  uint32_t* seg_bucket = (uint32_t*)ctx->ws_segbucket.p;
-  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)offsets, G, kSegLen, tsum);
-  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
-  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)offsets, G, kSegLen, tsum, seg_off, (uint32_t*)nullptr);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
   phase_mark(ctx, 2, st);
   const unsigned wgrid = (unsigned)std::min<size_t>((n * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
   B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, st, (const uint32_t*)digits, n, pl, cursor, idx);
   phase_mark(ctx, 3, st);
-  B2_LAUNCH(ctx, msm_accumulate<F>, (unsigned)((slices + 127) / 128), 128, 0, st, d_points, idx, offsets, seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
+  // batched-affine pair-summing rounds: each halves the entries the XYZZ accumulation has to fold
+  const uint32_t* cur_off = offsets;
+  const void* cur_pts = d_points;
+  for (uint32_t r = 1; r <= rounds; ++r) {
+    uint32_t* off_r = (uint32_t*)(r & 1 ? ctx->ws_pairoff1.p : ctx->ws_pairoff0.p);
+    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, r, tsum);
+    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, r, tsum, off_r, (uint32_t*)nullptr);
+    const size_t out_max = (M_max >> r) + G;
+    void* q = (r & 1) ? ctx->ws_q1.p : ctx->ws_q0.p;
+    const unsigned pgrid = (unsigned)((out_max / kPairBatch + 1 + 127) / 128);
+    if (r == 1) B2_LAUNCH(ctx, (pair_sum<F, true>), pgrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)off_r, (uint32_t)G, ctx->ws_prefix.p, (uint32_t*)ctx->ws_info.p, q);
+    else B2_LAUNCH(ctx, (pair_sum<F, false>), pgrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)off_r, (uint32_t)G, ctx->ws_prefix.p, (uint32_t*)ctx->ws_info.p, q);
+    cur_off = off_r;
+    cur_pts = q;
+  }
+  uint32_t* seg_off = (uint32_t*)ctx->ws_segoff.p;
+  uint32_t* seg_bucket = (uint32_t*)ctx->ws_segbucket.p;
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, cur_off, G, kSegLen, 0u, tsum);
+  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, cur_off, G, kSegLen, 0u, tsum, seg_off, (uint32_t*)nullptr);
+  if (rounds) B2_LAUNCH(ctx, (msm_accumulate<F, true>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
+  else B2_LAUNCH(ctx, (msm_accumulate<F, false>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
   {
-    // worst case every point of a window lands in one bucket: ceil(n / kSegLen) + 1 runs to fold
-    size_t worst = ((pl.merged ? n * (size_t)pl.W : n) + kSegLen - 1) / kSegLen + 1;
+    // worst case every point of a window lands in one bucket: ceil(entries / kSegLen) + 1 runs to fold
+    size_t worst_entries = ((pl.merged ? n * (size_t)pl.W : n) >> rounds) + 1;
+    size_t worst = (worst_entries + kSegLen - 1) / kSegLen + 1;
     for (size_t stride = 1; stride < worst; stride *= kTreeRadix)
       B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, seg_off, seg_bucket, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
   }

@@ -15,6 +15,7 @@
 // Ns*R <= 2^16 (a single lookup), else from two 4096-entry tables (w^lo, w^(hi*4096)): one extra
 // multiplication instead of an n/2-entry table streamed from HBM.
 #include "common.cuh"
+#include "tma.cuh"
 #include <cstdlib>
 #include <cstring>
 
@@ -102,6 +103,20 @@ B2_D void sts_fr(uint4* sm, uint32_t i, const Fr& a) {
   sm[2 * i + 1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
 }
 
+// v * w_{2^L}^(r*jm): one lookup when L <= 16, else two lookups and a product
+B2_D Fr interpass_twiddle(const Fr& v, uint32_t r, uint32_t jm, uint32_t k, uint32_t L, const NttTables& tb) {
+  const uint32_t x = r * jm;
+  if (!x) return v;
+  Fr tw;
+  if (L <= kDirectBits) {
+    tw = load_fe_nc<Fr>(tb.d16, x << (kDirectBits - L));
+  } else {
+    uint32_t e = x << (k - L);
+    tw = Fr::mul(load_fe_nc<Fr>(tb.lo, e & ((1u << kLoBits) - 1)), load_fe_nc<Fr>(tb.hi, e >> kLoBits));
+  }
+  return Fr::mul(v, tw);
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
   extern __shared__ uint4 sm[];
@@ -112,25 +127,22 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
   const uint32_t j0 = blockIdx.x << t;
   const uint32_t items = R << t;
 
-  // ---- load (+ inter-pass twiddle) : item -> (r, c), c fastest => 2^t * 32 B runs
-  for (uint32_t it = threadIdx.x; it < items; it += THREADS) {
-    uint32_t c = it & cmask, r = it >> t;
-    uint32_t j = j0 + c;
-    Fr v = load_fe<Fr>(a.in, (size_t)j + ((size_t)r << stride_log));
-    if (lns) {
-      const uint32_t x = r * (j & ns_mask), L = lns + s;  // twiddle = w_{2^L}^x
-      Fr tw;
-      if (L <= kDirectBits) {
-        tw = load_fe_nc<Fr>(a.tb.d16, x << (kDirectBits - L));
-      } else {
-        uint32_t e = x << (k - L);
-        tw = Fr::mul(load_fe_nc<Fr>(a.tb.lo, e & ((1u << kLoBits) - 1)), load_fe_nc<Fr>(a.tb.hi, e >> kLoBits));
-      }
-      if (x) v = Fr::mul(v, tw);
-    }
-    sts_fr(sm, it, v);  // sm[(r << t) + c]
-  }
+  // ---- load: the tile is R rows of 2^t * 32 contiguous bytes (one run when the tile is the whole input); the
+  // copy engine (cp.async.bulk, mbarrier completion) lands them in shared memory as sm[(r << t) + c]
+  __shared__ uint64_t tile_bar;
+  if (threadIdx.x == 0) { tma::barrier_init(&tile_bar, 1); tma::barrier_init_fence(); }
   __syncthreads();
+  {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.in);
+    if (threadIdx.x == 0) tma::barrier_expect(&tile_bar, items * 32u);
+    if (stride_log == t) {  // rows are adjacent in memory: one bulk copy
+      if (threadIdx.x == 0) tma::bulk_load(sm, src + (size_t)j0 * 32, items * 32u, &tile_bar);
+    } else {
+      for (uint32_t r = threadIdx.x; r < R; r += THREADS)
+        tma::bulk_load(sm + 2 * ((size_t)r << t), src + ((size_t)j0 + ((size_t)r << stride_log)) * 32, cols * 32u, &tile_bar);
+    }
+    tma::barrier_wait(&tile_bar, 0);
+  }
 
   // ---- s decimation-in-frequency stages in shared memory
   const uint4* stage_tw = a.tb.stage + 2 * ((size_t)(R >> 1) - 1);
@@ -149,6 +161,10 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
       uint32_t i = (blk << (lm + 1)) | jj;
       uint32_t p0 = (i << t) + c, p1 = ((i + m) << t) + c;
       Fr x = lds_fr(sm, p0), y = lds_fr(sm, p1);
+      if (q == 0 && lns) {  // inter-pass twiddles w_{2^L}^(r * (j mod Ns)), applied as the rows are first touched
+        x = interpass_twiddle(x, i, (j0 + c) & ns_mask, k, lns + s, a.tb);
+        y = interpass_twiddle(y, i + m, (j0 + c) & ns_mask, k, lns + s, a.tb);
+      }
       Fr d = Fr::sub(x, y);
       if (jj) d = Fr::mul(d, load_fe_nc<Fr>(stage_tw, jj << q));
       sts_fr(sm, p0, Fr::add(x, y));

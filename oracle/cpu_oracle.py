@@ -64,8 +64,25 @@ def array_to_ints(a: np.ndarray):
     return [limbs_to_int(row) for row in a.reshape(-1, 4)]
 
 
+def effective_cpus() -> int:
+    """CPUs this process can really use: min(affinity mask, cgroup cpu.max quota).  Spawning one OpenMP
+    thread per *visible* core under a smaller cgroup quota oversubscribes and runs slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
 def num_threads() -> int:
-    return lib().orc_num_threads()
+    return min(lib().orc_num_threads(), effective_cpus())
+
+
+def _thr(threads: int) -> int:
+    return threads if threads > 0 else num_threads()
 
 
 def rand_fr(seed: int, start: int, n: int) -> np.ndarray:
@@ -107,13 +124,13 @@ def field_mul(field: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
 
 def g1_chain(n: int, k: int, d: int, threads: int = 0) -> np.ndarray:
     out = np.empty((n, 8), dtype=np.uint64)
-    lib().orc_g1_chain(_p(out), C.c_size_t(n), _p(int_to_limbs(k)), _p(int_to_limbs(d)), C.c_int(threads))
+    lib().orc_g1_chain(_p(out), C.c_size_t(n), _p(int_to_limbs(k)), _p(int_to_limbs(d)), C.c_int(_thr(threads)))
     return out
 
 
 def g2_chain(n: int, k: int, d: int, threads: int = 0) -> np.ndarray:
     out = np.empty((n, 16), dtype=np.uint64)
-    lib().orc_g2_chain(_p(out), C.c_size_t(n), _p(int_to_limbs(k)), _p(int_to_limbs(d)), C.c_int(threads))
+    lib().orc_g2_chain(_p(out), C.c_size_t(n), _p(int_to_limbs(k)), _p(int_to_limbs(d)), C.c_int(_thr(threads)))
     return out
 
 
@@ -177,7 +194,7 @@ def g1_msm(points: np.ndarray, scalars: np.ndarray, method: int = 0, threads: in
     n = scalars.size // 4
     assert points.size // 8 >= n
     buf = C.create_string_buffer(64)
-    lib().orc_g1_msm(_p(points), _p(scalars), C.c_size_t(n), C.c_int(method), C.c_int(threads), buf)
+    lib().orc_g1_msm(_p(points), _p(scalars), C.c_size_t(n), C.c_int(method), C.c_int(_thr(threads)), buf)
     return buf.raw
 
 
@@ -185,7 +202,7 @@ def g2_msm(points: np.ndarray, scalars: np.ndarray, method: int = 0, threads: in
     n = scalars.size // 4
     assert points.size // 16 >= n
     buf = C.create_string_buffer(128)
-    lib().orc_g2_msm(_p(points), _p(scalars), C.c_size_t(n), C.c_int(method), C.c_int(threads), buf)
+    lib().orc_g2_msm(_p(points), _p(scalars), C.c_size_t(n), C.c_int(method), C.c_int(_thr(threads)), buf)
     return buf.raw
 
 
@@ -199,7 +216,7 @@ def fr_ntt(data_mont: np.ndarray, log_n: int, flags: int = 0, coset_gen: int | N
     assert a.size // 4 == 1 << log_n
     cg = _p(int_to_limbs(coset_gen)) if coset_gen is not None else None
     rt = _p(int_to_limbs(root_2_28)) if root_2_28 is not None else None
-    rc = lib().orc_fr_ntt(_p(a), C.c_uint(log_n), C.c_uint(flags), cg, rt, C.c_int(threads))
+    rc = lib().orc_fr_ntt(_p(a), C.c_uint(log_n), C.c_uint(flags), cg, rt, C.c_int(_thr(threads)))
     if rc:
         raise ValueError(f"ntt status {rc}")
     return a
