@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200zk_field_to_mont_device": (_int, [_ctx, _vp, _sz, _int, _vp]),
     "b200zk_field_from_mont_device": (_int, [_ctx, _vp, _sz, _int, _vp]),
     "b200zk_field_mul_device": (_int, [_ctx, _vp, _vp, _vp, _sz, _int, _u32, _vp]),
+    "b200zk_fr_quotient_device": (_int, [_ctx, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "b200zk_fr_random_device": (_int, [_ctx, _vp, _sz, _u64, _u64, _u32, _vp]),
     "b200zk_g1_chain_device": (_int, [_ctx, _vp, _sz, _sz, _vp, _vp, _vp]),
     "b200zk_g2_chain_device": (_int, [_ctx, _vp, _sz, _sz, _vp, _vp, _vp]),

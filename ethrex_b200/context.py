@@ -232,6 +232,11 @@ class Context:
     def field_mul_device(self, d_a, d_b, d_out, n: int, which: int, repeat: int = 1):
         self._check(F.lib.b200zk_field_mul_device(self._h, _dev_ptr(d_a), _dev_ptr(d_b), _dev_ptr(d_out), n, which, repeat, _current_stream_ptr()), "field_mul")
 
+    def fr_quotient_device(self, d_a, d_b, d_c, d_out, n: int, zinv: int):
+        """d_out[i] = (a[i]*b[i] - c[i]) * zinv (Montgomery data, zinv an integer mod r)."""
+        z = C.cast(C.c_char_p(int(zinv).to_bytes(32, "little")), C.c_void_p)
+        self._check(F.lib.b200zk_fr_quotient_device(self._h, _dev_ptr(d_a), _dev_ptr(d_b), _dev_ptr(d_c), _dev_ptr(d_out), n, z, _current_stream_ptr()), "fr_quotient")
+
     def fr_random_device(self, d_out, n: int, seed: int, start: int = 0, flags: int = 0):
         self._check(F.lib.b200zk_fr_random_device(self._h, _dev_ptr(d_out), n, seed, start, flags, _current_stream_ptr()), "fr_random")
 

@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ p
 // y3) products + 1/kPairBatch of an inversion  ~ 6.7 products, against 10 for an XYZZ mixed addition; after r
 // rounds the XYZZ accumulation only sees M/2^r entries.  Exceptional pairs (equal points -> tangent, opposite
 // points -> identity, identity operands) put 1 (or 2y) in the batch and are resolved in the backward sweep.
-static constexpr uint32_t kPairBatch = 512;
+static constexpr uint32_t kPairBatch = 256;
 
 template <class F, bool INDIRECT>
 B2_D Affine<F> pair_load(const void* __restrict__ points, const uint32_t* __restrict__ idx, uint32_t e) {
@@ -363,6 +363,19 @@ template <class F> B2_D F pair_denominator(const Affine<F>& a, const Affine<F>& 
   *kind = 4; return F::one();
 }
 
+// x coordinates only (the forward sweep needs no y unless the x's collide)
+template <class F, bool INDIRECT>
+B2_D void pair_load_x(const void* __restrict__ points, const uint32_t* __restrict__ idx, uint32_t e, F* x, uint32_t* v) {
+  *v = INDIRECT ? __ldg(idx + e) : e;
+  *x = load_field_nc(points, 2 * (size_t)(*v & 0x7fffffffu), (const F*)nullptr);
+}
+template <class F, bool INDIRECT>
+B2_D F pair_load_y(const void* __restrict__ points, uint32_t v) {
+  F y = load_field_nc(points, 2 * (size_t)(v & 0x7fffffffu) + 1, (const F*)nullptr);
+  if (INDIRECT && (v >> 31)) y = F::neg(y);
+  return y;
+}
+
 template <class F, bool INDIRECT>
 __global__ void __launch_bounds__(128) pair_sum(const void* __restrict__ points, const uint32_t* __restrict__ idx,
                                                 const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t G,
@@ -381,49 +394,76 @@ __global__ void __launch_bounds__(128) pair_sum(const void* __restrict__ points,
   }
   uint32_t next = __ldg(off_out + g + 1);
   uint32_t base_out = __ldg(off_out + g), base_in = __ldg(off_in + g), end_in = __ldg(off_in + g + 1);
-  // forward sweep: prefix products of the denominators
-  F prod = F::one();
-  for (uint32_t o = o0; o < o1; ++o) {
+  // ---- forward sweep: prefix products of the denominators.  The (entry, has_pair) word of every output is
+  // computed one iteration ahead so that the x gathers of output o+1 are in flight during the product of output o.
+  auto locate = [&](uint32_t o) -> uint32_t {
     if (o == next) {
       g = bucket_of(off_out, G, g + 1, o);
       next = __ldg(off_out + g + 1);
       base_out = __ldg(off_out + g); base_in = __ldg(off_in + g); end_in = __ldg(off_in + g + 1);
     }
     const uint32_t ea = base_in + 2 * (o - base_out);
-    const bool has_pair = ea + 1 < end_in;
-    info[o] = ea | (has_pair ? 0x80000000u : 0u);
-    store_field(prefix, o, prod);
-    if (has_pair) {
-      Affine<F> a = pair_load<F, INDIRECT>(points, idx, ea), b = pair_load<F, INDIRECT>(points, idx, ea + 1);
-      int kind;
-      F d = pair_denominator(a, b, &kind);
-      if (kind <= 1) prod = F::mul(prod, d);
+    return ea | ((ea + 1 < end_in) ? 0x80000000u : 0u);
+  };
+  F prod = F::one();
+  uint32_t w = locate(o0), va = 0, vb = 0;
+  F xa = F::zero(), xb = F::zero();
+  pair_load_x<F, INDIRECT>(points, idx, w & 0x7fffffffu, &xa, &va);
+  if (w >> 31) pair_load_x<F, INDIRECT>(points, idx, (w & 0x7fffffffu) + 1, &xb, &vb);
+  for (uint32_t o = o0; o < o1; ++o) {
+    uint32_t wn = w, van = va, vbn = vb; F xan = xa, xbn = xb;
+    if (o + 1 < o1) {
+      wn = locate(o + 1);
+      pair_load_x<F, INDIRECT>(points, idx, wn & 0x7fffffffu, &xan, &van);
+      if (wn >> 31) pair_load_x<F, INDIRECT>(points, idx, (wn & 0x7fffffffu) + 1, &xbn, &vbn);
     }
+    info[o] = w;
+    store_field(prefix, o, prod);
+    if (w >> 31) {
+      F d = F::sub(xb, xa);
+      bool plain = !d.is_zero();
+      if (!plain || xa.is_zero() || xb.is_zero()) {  // rare: equal x, or a possible identity operand -> full classification
+        Affine<F> a = {xa, pair_load_y<F, INDIRECT>(points, va)}, b = {xb, pair_load_y<F, INDIRECT>(points, vb)};
+        int kind;
+        d = pair_denominator(a, b, &kind);
+        plain = kind <= 1;
+      }
+      if (plain) prod = F::mul(prod, d);
+    }
+    w = wn; va = van; vb = vbn; xa = xan; xb = xbn;
   }
   F inv = F::inv(prod);
-  // backward sweep
+  // ---- backward sweep (next pair's four coordinates prefetched the same way)
+  uint32_t wo = info[o1 - 1];
+  Affine<F> a = pair_load<F, INDIRECT>(points, idx, wo & 0x7fffffffu), b = a;
+  if (wo >> 31) b = pair_load<F, INDIRECT>(points, idx, (wo & 0x7fffffffu) + 1);
+  F pre = load_field(prefix, o1 - 1, (const F*)nullptr);
   for (uint32_t o = o1; o-- > o0;) {
-    const uint32_t w = info[o];
-    const uint32_t ea = w & 0x7fffffffu;
-    Affine<F> a = pair_load<F, INDIRECT>(points, idx, ea);
-    if (!(w >> 31)) { store_affine<F>(out, o, a); continue; }
-    Affine<F> b = pair_load<F, INDIRECT>(points, idx, ea + 1);
-    int kind;
-    F d = pair_denominator(a, b, &kind);
-    Affine<F> r;
-    if (kind <= 1) {
-      F dinv = F::mul(inv, load_field(prefix, o, (const F*)nullptr));  // 1/d
-      inv = F::mul(inv, d);
-      F num;
-      if (kind == 0) num = F::sub(b.y, a.y);
-      else { F xx = F::sqr(a.x); num = F::add(F::dbl(xx), xx); }
-      F lam = F::mul(num, dinv);
-      r.x = F::sub(F::sub(F::sqr(lam), a.x), b.x);
-      r.y = F::sub(F::mul(lam, F::sub(a.x, r.x)), a.y);
-    } else if (kind == 2) r = a;
-    else if (kind == 3) r = b;
-    else r = {F::zero(), F::zero()};
+    uint32_t won = wo; Affine<F> an = a, bn = b; F pren = pre;
+    if (o > o0) {
+      won = info[o - 1];
+      an = pair_load<F, INDIRECT>(points, idx, won & 0x7fffffffu);
+      if (won >> 31) bn = pair_load<F, INDIRECT>(points, idx, (won & 0x7fffffffu) + 1);
+      pren = load_field(prefix, o - 1, (const F*)nullptr);
+    }
+    Affine<F> r = a;
+    if (wo >> 31) {
+      int kind;
+      F d = pair_denominator(a, b, &kind);
+      if (kind <= 1) {
+        F dinv = F::mul(inv, pre);  // 1/d
+        inv = F::mul(inv, d);
+        F num;
+        if (kind == 0) num = F::sub(b.y, a.y);
+        else { F xx = F::sqr(a.x); num = F::add(F::dbl(xx), xx); }
+        F lam = F::mul(num, dinv);
+        r.x = F::sub(F::sub(F::sqr(lam), a.x), b.x);
+        r.y = F::sub(F::mul(lam, F::sub(a.x, r.x)), a.y);
+      } else if (kind == 3) r = b;
+      else if (kind == 4) r = {F::zero(), F::zero()};
+    }
     store_affine<F>(out, o, r);
+    wo = won; a = an; b = bn; pre = pren;
   }
 }
 
@@ -556,10 +596,12 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_TRY(ensure(ctx, ctx->ws_idx, n * (size_t)pl.W * 4));
   B2_TRY(ensure(ctx, ctx->ws_digits, n * (size_t)pl.W * 4));
   const size_t M_max = n * (size_t)pl.W;
-  // pair-summing rounds (auto: worth it once buckets hold a few dozen entries on average)
+  // pair-summing rounds.  Measured on B200 (profiles/r1_pair_sum.md): a round costs ~180 ps per pair (it is
+  // bound by its ~330 B of scattered memory traffic per pair, not by its 6.7 products) against the ~158 ps XYZZ
+  // addition it removes, so the automatic setting is OFF; the path stays available (b200zk_set_msm_pair_rounds)
+  // for parts with a different compute:bandwidth balance and is covered by the parity tests.
   uint32_t rounds = 0;
   if (ctx->msm_pair_rounds >= 0) rounds = (uint32_t)ctx->msm_pair_rounds;
-  else { size_t avg = M_max / G; rounds = avg >= 96 ? 2 : (avg >= 24 ? 1 : 0); }
   if (rounds > 4) rounds = 4;
   if (rounds && M_max >= ((size_t)1 << 31)) rounds = 0;
   const size_t S_max = (M_max >> rounds) / kSegLen + 1 + G;  // upper bound on the number of runs

@@ -38,6 +38,19 @@ __global__ void __launch_bounds__(256) field_mul_kernel(const void* a, const voi
   }
 }
 
+// out[i] = (a[i]*b[i] - c[i]) * zinv : the Groth16 quotient numerator on the coset, divided by the (constant)
+// vanishing polynomial value h^n - 1.  All Montgomery form; zinv given canonical.
+__global__ void __launch_bounds__(256) fr_quotient(const void* a, const void* b, const void* c, void* out, size_t n, const uint32_t* zinv_canonical) {
+  Fr z;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) z.v[k] = zinv_canonical[k];
+  z = Fr::to_mont(z);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr t = Fr::sub(Fr::mul(load_fe<Fr>(a, i), load_fe<Fr>(b, i)), load_fe<Fr>(c, i));
+    store_fe<Fr>(out, i, Fr::mul(t, z));
+  }
+}
+
 // ---- splitmix64 counter generator (identical to oracle/pyref.py rand_fr and the C++ oracle) -----------------------
 B2_D uint64_t splitmix64(uint64_t& st) {
   st += 0x9E3779B97F4A7C15ull;
@@ -191,6 +204,17 @@ int b200zk_field_mul_device(b200zk_ctx* ctx, const void* a, const void* b, void*
   unsigned grid = (unsigned)((n + 255) / 256);
   if (which == 0) B2_LAUNCH(ctx, field_mul_kernel<Fq>, grid, 256, 0, st, a, b, out, n, repeat);
   else B2_LAUNCH(ctx, field_mul_kernel<Fr>, grid, 256, 0, st, a, b, out, n, repeat);
+  return B200ZK_OK;
+}
+int b200zk_fr_quotient_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n, const uint8_t zinv[32], void* stream) {
+  if (!ctx || !zinv || ((!d_a || !d_b || !d_c || !d_out) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "fr_quotient: null argument");
+  cudaStream_t st = pick_stream(ctx, stream);
+  if (!n) return B200ZK_OK;
+  B2_TRY(ensure(ctx, ctx->ws_misc, 512));
+  memcpy(ctx->h_pinned + 3072, zinv, 32);
+  B2_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ctx->ws_misc.p + 384, ctx->h_pinned + 3072, 32, cudaMemcpyHostToDevice, st));
+  B2_LAUNCH(ctx, fr_quotient, egrid(ctx, n, 256), 256, 0, st, d_a, d_b, d_c, d_out, n, (const uint32_t*)((uint8_t*)ctx->ws_misc.p + 384));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));  // staging buffers are reused by the next call
   return B200ZK_OK;
 }
 int b200zk_fr_random_device(b200zk_ctx* ctx, void* d_out, size_t n, uint64_t seed, uint64_t start, uint32_t flags, void* stream) {

@@ -163,6 +163,10 @@ int b200zk_field_from_mont_device(b200zk_ctx* ctx, void* d_data, size_t n, int w
  * `repeat` > 1 chains out = out * b that many times (throughput measurement) */
 int b200zk_field_mul_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, void* d_out, size_t n,
                             int which, uint32_t repeat, void* stream);
+/* out[i] = (a[i]*b[i] - c[i]) * zinv over Fr (Montgomery data; zinv canonical LE): the pointwise step of the
+ * Groth16 quotient H = (A*B - C)/Z_H evaluated on a coset, where Z_H is the constant h^n - 1 */
+int b200zk_fr_quotient_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out,
+                              size_t n, const uint8_t zinv[32], void* stream);
 /* counter-based splitmix64 scalars: element i = reduce_mod_r(4 outputs of state seed + 4*(start+i)*golden)
  * (SURVEY.md 8d); canonical limbs, or Montgomery with B200ZK_SCALARS_MONT */
 int b200zk_fr_random_device(b200zk_ctx* ctx, void* d_out, size_t n, uint64_t seed, uint64_t start,

@@ -79,6 +79,7 @@ unsafe extern "C" {
     pub fn b200zk_field_to_mont_device(ctx: *mut b200zk_ctx, d_data: *mut c_void, n: usize, which: c_int, stream: *mut c_void) -> c_int;
     pub fn b200zk_field_from_mont_device(ctx: *mut b200zk_ctx, d_data: *mut c_void, n: usize, which: c_int, stream: *mut c_void) -> c_int;
     pub fn b200zk_field_mul_device(ctx: *mut b200zk_ctx, d_a: *const c_void, d_b: *const c_void, d_out: *mut c_void, n: usize, which: c_int, repeat: u32, stream: *mut c_void) -> c_int;
+    pub fn b200zk_fr_quotient_device(ctx: *mut b200zk_ctx, d_a: *const c_void, d_b: *const c_void, d_c: *const c_void, d_out: *mut c_void, n: usize, zinv: *const u8, stream: *mut c_void) -> c_int;
     pub fn b200zk_fr_random_device(ctx: *mut b200zk_ctx, d_out: *mut c_void, n: usize, seed: u64, start: u64, flags: u32, stream: *mut c_void) -> c_int;
     pub fn b200zk_g1_chain_device(ctx: *mut b200zk_ctx, d_out: *mut c_void, start: usize, n: usize, k: *const u8, d: *const u8, stream: *mut c_void) -> c_int;
     pub fn b200zk_g2_chain_device(ctx: *mut b200zk_ctx, d_out: *mut c_void, start: usize, n: usize, k: *const u8, d: *const u8, stream: *mut c_void) -> c_int;

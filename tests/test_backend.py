@@ -1,0 +1,79 @@
+"""B200Backend: the ProverBackend mirror (CPU-side behaviour) and, on a GPU, the Groth16-shaped pipeline
+against the same pipeline computed with the CPU oracle."""
+import numpy as np
+import pytest
+
+import cpu_oracle as orc
+import pyref
+import ethrex_b200 as eb
+from ethrex_b200.backend import B200Backend, BackendType, ProofFormat, ProverType, serialize_program_input
+from ethrex_b200.groth16 import COSET_GEN, SyntheticWrapCircuit, _chain_kd, _seed64
+
+
+def test_backend_without_circuit_mirrors_reference_errors():
+    """error behaviour of a ProverBackend without its SDK (backend/mod.rs:81-147, error.rs:3-51)."""
+    b = B200Backend()
+    assert b.prover_type() is ProverType.EXEC
+    assert BackendType.from_str("B200") is BackendType.B200 and BackendType.from_str("exec") is BackendType.EXEC
+    with pytest.raises(ValueError, match="Invalid backend"):
+        BackendType.from_str("sp2")
+    with pytest.raises(eb.B200Error) as e:
+        b.prove({"blocks": []})
+    assert e.value.kind == "NotImplemented"
+    with pytest.raises(eb.B200Error) as e:
+        b.prove(b"x", ProofFormat.COMPRESSED)
+    assert e.value.kind == "NotImplemented"
+    with pytest.raises(eb.B200Error, match="Verify not implemented for this backend"):
+        b.verify(None)
+    with pytest.raises(eb.B200Error) as e:
+        b.serialize_input({"x": object()})
+    assert e.value.kind == "Serialization"
+    assert serialize_program_input({"b": 1, "a": [2]}) == b'{"a":[2],"b":1}'
+    s, dt = b.serialize_input_timed(b"abc")
+    assert s == b"abc" and dt >= 0
+    assert b.execute_timed(b"abc") >= 0
+
+
+@pytest.mark.gpu
+def test_groth16_pipeline_matches_oracle(ctx):
+    """config #5 at 2^10: quotient (7 NTTs + pointwise) and the five MSMs, byte for byte."""
+    log_n, n = 10, 1 << 10
+    circuit = SyntheticWrapCircuit(ctx, log_n, precompute=True)
+    backend = B200Backend(ctx, circuit)
+    try:
+        inp = {"blocks": [1, 2, 3], "elasticity_multiplier": 2}
+        proof, dt = backend.prove_timed(inp, ProofFormat.GROTH16)
+        out = backend.to_proof_bytes(proof, ProofFormat.GROTH16)
+        assert out.prover_type() is ProverType.SP1 and len(out.proof_bytes.proof) == 256
+        # ---- the same pipeline on the CPU oracle
+        ser = backend.serialize_input(inp)
+        w = orc.rand_fr(_seed64(ser, b"witness"), 0, n)
+        a = orc.fr_to_mont(orc.rand_fr(_seed64(ser, b"A"), 0, n))
+        b = orc.fr_to_mont(orc.rand_fr(_seed64(ser, b"B"), 0, n))
+        c = orc.field_mul("fr", a, b)
+        cos = []
+        for poly in (a, b, c):
+            coeff = orc.fr_ntt(poly, log_n, orc.NTT_INVERSE)
+            cos.append(orc.array_to_ints(orc.fr_from_mont(orc.fr_ntt(coeff, log_n, orc.NTT_COSET))))
+        zinv = pow((pow(COSET_GEN, n, pyref.R) - 1) % pyref.R, -1, pyref.R)
+        hq = [((x * y - z) * zinv) % pyref.R for x, y, z in zip(*cos)]
+        h = orc.fr_ntt(orc.fr_to_mont(orc.ints_to_array(hq)), log_n, orc.NTT_INVERSE | orc.NTT_COSET)
+        h_can = orc.fr_from_mont(h)
+        assert orc.array_to_ints(h_can)[n - 1] == 0  # deg H < n-1: the quotient is exact
+        exp = {}
+        for name, is_g2 in SyntheticWrapCircuit.QUERIES:
+            k, d = _chain_kd(name.encode())
+            sc, cnt = (h_can, n - 1) if name == "h_g1" else (w, n)
+            if is_g2:
+                exp[name] = orc.g2_msm(orc.g2_chain(n, k, d)[:cnt], sc[:cnt])
+            else:
+                exp[name] = orc.g1_msm(orc.g1_chain(n, k, d)[:cnt], sc[:cnt])
+        for name in exp:
+            assert proof.commitments[name] == exp[name], name
+        c_pt = orc.g1_add_be(exp["l_g1"], exp["h_g1"])[1]
+        assert proof.proof == exp["a_g1"] + exp["b_g2"] + c_pt
+        # deterministic: same input, same proof; different input, different proof
+        assert backend.prove(inp).proof == proof.proof
+        assert backend.prove({"blocks": [9]}).proof != proof.proof
+    finally:
+        circuit.close()

@@ -419,3 +419,38 @@ def test_precomputed_2_20_closed_form(ctx):
         assert ctx.g1_msm_resident_device(h, ds, n) == expected_chain_msm_g1(to_host(ds).reshape(n, 4), k, d)
     finally:
         ctx.bases_free(h)
+
+
+def test_pair_sum_rounds_edge_cases(ctx):
+    """batched-affine pre-pass: equal points (tangent), opposite points (identity), identity operands, heavy buckets."""
+    k, d = chain_kd()
+    n = 4096
+    pts = orc.g1_chain(n, k, d)
+    pts[1] = pts[0]; pts[3] = pts[2]; pts[9] = pts[8]                       # repeated bases
+    neg = orc.g1_be_to_native(pyref.g1_to_be(pyref.pt_neg(pyref._Fq, pyref.g1_from_be(orc.g1_native_to_be(pts[4:5])))))
+    pts[5] = neg[0]                                                          # P and -P
+    pts[7] = 0; pts[11] = 0                                                  # identity bases
+    cases = {
+        "random": scalars_special(n),
+        "all_one": orc.ints_to_array([1] * n),                               # one heavy bucket, every pair in it
+        "all_same": orc.ints_to_array([0x1234567] * n),
+        "pairs": orc.ints_to_array([(i // 2) * 7919 + 1 for i in range(n)]),  # neighbours share their digits
+    }
+    dp = to_dev(pts)
+    try:
+        for c in (6, 11):
+            ctx.set_msm_window(c)
+            for rounds in (1, 2, 3, 4):
+                ctx.set_msm_pair_rounds(rounds)
+                for name, s in cases.items():
+                    assert ctx.g1_msm_device(dp, to_dev(s), n) == orc.g1_msm(pts, s), (c, rounds, name)
+        ctx.set_msm_window(0)
+        pts2 = orc.g2_chain(512, k, d)
+        pts2[1] = pts2[0]
+        s2 = orc.ints_to_array([3] * 512)
+        for rounds in (1, 3):
+            ctx.set_msm_pair_rounds(rounds)
+            assert ctx.g2_msm_device(to_dev(pts2), to_dev(s2), 512) == orc.g2_msm(pts2, s2)
+    finally:
+        ctx.set_msm_window(0)
+        ctx.set_msm_pair_rounds(-1)
