@@ -89,8 +89,19 @@ struct PassArgs {
   void* out;
   uint32_t log_n, s, t, log_ns;
   uint32_t scale_out;  // multiply outputs by n^-1
+  uint32_t coset_in;   // first pass of a forward coset transform: element i enters multiplied by h^i
+  uint32_t coset_out;  // last pass of an inverse coset transform: element i leaves multiplied by h^-i * n^-1
+  const uint4* c_lo;   // coset powers, low table  (base^x, x < 4096; the inverse one carries n^-1)
+  const uint4* c_hi;   // coset powers, high table (base^(y << 12))
   NttTables tb;
 };
+
+// v * base^i from the two-level coset tables
+B2_D Fr coset_scale(const Fr& v, size_t i, uint32_t k, const uint4* lo, const uint4* hi) {
+  Fr tw = load_fe_nc<Fr>(lo, i & ((1u << kLoBits) - 1));
+  if (k > (uint32_t)kLoBits) tw = Fr::mul(tw, load_fe_nc<Fr>(hi, i >> kLoBits));
+  return Fr::mul(v, tw);
+}
 
 B2_D Fr lds_fr(const uint4* sm, uint32_t i) {
   uint4 lo = sm[2 * i], hi = sm[2 * i + 1];
@@ -117,8 +128,8 @@ B2_D Fr interpass_twiddle(const Fr& v, uint32_t r, uint32_t jm, uint32_t k, uint
   return Fr::mul(v, tw);
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) ntt_pass(PassArgs a) {
   extern __shared__ uint4 sm[];
   const uint32_t k = a.log_n, s = a.s, t = a.t, lns = a.log_ns;
   const uint32_t R = 1u << s, cols = 1u << t, cmask = cols - 1;
@@ -144,31 +155,56 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
     tma::barrier_wait(&tile_bar, 0);
   }
 
-  // ---- s decimation-in-frequency stages in shared memory
+  // ---- s decimation-in-frequency stages in shared memory, two stages per round trip (radix-4 in registers):
+  // a thread holds rows {i, i+m/2, i+m, i+3m/2}, does the stage-q butterflies (i,i+m), (i+m/2,i+3m/2) and then
+  // the stage-(q+1) butterflies (i,i+m/2), (i+m,i+3m/2) before anything goes back to shared memory -- half the
+  // LDS/STS traffic and half the barriers of a stage-by-stage sweep.  An odd s starts with one radix-2 stage.
   const uint4* stage_tw = a.tb.stage + 2 * ((size_t)(R >> 1) - 1);
-  const uint32_t half_items = items >> 1;
-  for (uint32_t q = 0; q < s; ++q) {
-    const uint32_t lm = s - 1 - q, m = 1u << lm;
-    // Butterfly u of this stage = (block, jj) with twiddle w_{2m}^jj.  Where possible jj is taken from the HIGH
-    // bits of u, so that the lanes of a warp share one jj: the twiddle load is a broadcast and the jj == 0
-    // butterflies (twiddle 1: half of them at m = 2, a quarter at m = 4, ...) skip the product warp-uniformly.
-    const bool uniform = lm + 3 <= s;
-    const uint32_t hb = s - 1 - lm;
-    for (uint32_t it = threadIdx.x; it < half_items; it += THREADS) {
-      uint32_t c = it & cmask, u = it >> t;
-      uint32_t jj = uniform ? (u >> hb) : (u & (m - 1));
-      uint32_t blk = uniform ? (u & ((1u << hb) - 1)) : (u >> lm);
-      uint32_t i = (blk << (lm + 1)) | jj;
-      uint32_t p0 = (i << t) + c, p1 = ((i + m) << t) + c;
-      Fr x = lds_fr(sm, p0), y = lds_fr(sm, p1);
-      if (q == 0 && lns) {  // inter-pass twiddles w_{2^L}^(r * (j mod Ns)), applied as the rows are first touched
-        x = interpass_twiddle(x, i, (j0 + c) & ns_mask, k, lns + s, a.tb);
-        y = interpass_twiddle(y, i + m, (j0 + c) & ns_mask, k, lns + s, a.tb);
-      }
+  auto first_touch = [&](Fr v, uint32_t row, uint32_t c) -> Fr {
+    if (a.coset_in) v = coset_scale(v, (size_t)(j0 + c) + ((size_t)row << stride_log), k, a.c_lo, a.c_hi);  // h^index
+    if (lns) v = interpass_twiddle(v, row, (j0 + c) & ns_mask, k, lns + s, a.tb);  // w_{2^L}^(row * (j mod Ns))
+    return v;
+  };
+  uint32_t q = 0;
+  if (s & 1) {
+    const uint32_t lm = s - 1, m = 1u << lm;
+    for (uint32_t it = threadIdx.x; it < (items >> 1); it += THREADS) {
+      uint32_t c = it & cmask, jj = it >> t;  // one block: blk = 0
+      uint32_t p0 = (jj << t) + c, p1 = ((jj + m) << t) + c;
+      Fr x = first_touch(lds_fr(sm, p0), jj, c), y = first_touch(lds_fr(sm, p1), jj + m, c);
       Fr d = Fr::sub(x, y);
-      if (jj) d = Fr::mul(d, load_fe_nc<Fr>(stage_tw, jj << q));
+      if (jj) d = Fr::mul(d, load_fe_nc<Fr>(stage_tw, jj));
       sts_fr(sm, p0, Fr::add(x, y));
       sts_fr(sm, p1, d);
+    }
+    __syncthreads();
+    q = 1;
+  }
+  for (; q < s; q += 2) {
+    const uint32_t lm = s - 1 - q, m = 1u << lm, m2 = m >> 1;
+    // quad u = (block, jj), jj < m/2.  With jj in the HIGH bits of u the lanes of a warp share one jj: twiddle
+    // loads are broadcasts and the jj == 0 quads (w^0 = 1 on three of their four products) skip them warp-uniformly.
+    const uint32_t nblk_log = q;             // R / (2m) blocks
+    const bool uniform = nblk_log >= 2;
+    for (uint32_t it = threadIdx.x; it < (items >> 2); it += THREADS) {
+      uint32_t c = it & cmask, u = it >> t;
+      uint32_t jj = uniform ? (u >> nblk_log) : (u & (m2 - 1));
+      uint32_t blk = uniform ? (u & ((1u << nblk_log) - 1)) : (u >> (lm - 1));
+      uint32_t i = (blk << (lm + 1)) | jj;
+      uint32_t pa = (i << t) + c, pb = ((i + m2) << t) + c, pc = ((i + m) << t) + c, pd = ((i + m + m2) << t) + c;
+      Fr A = lds_fr(sm, pa), B = lds_fr(sm, pb), C = lds_fr(sm, pc), D = lds_fr(sm, pd);
+      if (q == 0) { A = first_touch(A, i, c); B = first_touch(B, i + m2, c); C = first_touch(C, i + m, c); D = first_touch(D, i + m + m2, c); }
+      // stage q: distance m, twiddles w_{2m}^jj and w_{2m}^(jj + m/2)
+      Fr t0 = Fr::add(A, C), t1 = Fr::sub(A, C), t2 = Fr::add(B, D), t3 = Fr::sub(B, D);
+      if (jj) t1 = Fr::mul(t1, load_fe_nc<Fr>(stage_tw, jj << q));
+      t3 = Fr::mul(t3, load_fe_nc<Fr>(stage_tw, (jj + m2) << q));
+      // stage q+1: distance m/2, twiddle w_m^jj for both butterflies
+      Fr o0 = Fr::add(t0, t2), o1 = Fr::sub(t0, t2), o2 = Fr::add(t1, t3), o3 = Fr::sub(t1, t3);
+      if (jj) {
+        Fr w = load_fe_nc<Fr>(stage_tw, jj << (q + 1));
+        o1 = Fr::mul(o1, w); o3 = Fr::mul(o3, w);
+      }
+      sts_fr(sm, pa, o0); sts_fr(sm, pb, o1); sts_fr(sm, pc, o2); sts_fr(sm, pd, o3);
     }
     __syncthreads();
   }
@@ -181,8 +217,10 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
       uint32_t q = it & (R - 1), c = it >> s;
       uint32_t row = s ? (__brev(q) >> (32 - s)) : 0;
       Fr v = lds_fr(sm, (row << t) + c);
+      const size_t o = (((size_t)(j0 + c)) << s) + q;
       if (a.scale_out) v = Fr::mul(v, ninv);
-      store_fe<Fr>(a.out, (((size_t)(j0 + c)) << s) + q, v);
+      if (a.coset_out) v = coset_scale(v, o, k, a.c_lo, a.c_hi);
+      store_fe<Fr>(a.out, o, v);
     }
   } else {
     for (uint32_t it = threadIdx.x; it < items; it += THREADS) {
@@ -192,6 +230,7 @@ __global__ void __launch_bounds__(THREADS) ntt_pass(PassArgs a) {
       Fr v = lds_fr(sm, (row << t) + c);
       if (a.scale_out) v = Fr::mul(v, ninv);
       size_t o = (((size_t)(j >> lns)) << (lns + s)) + (j & ns_mask) + ((size_t)q << lns);
+      if (a.coset_out) v = coset_scale(v, o, k, a.c_lo, a.c_hi);
       store_fe<Fr>(a.out, o, v);
     }
   }
@@ -300,12 +339,20 @@ static int launch_pass(b200zk_ctx* ctx, const PassArgs& a, cudaStream_t st) {
   const unsigned grid = 1u << (a.log_n - a.s - a.t);
   if (items >= 4096) {
     static bool attr512 = false;
-    if (!attr512) { B2_CUDA(ctx, cudaFuncSetAttribute(ntt_pass<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 17)); attr512 = true; }
-    B2_LAUNCH(ctx, ntt_pass<512>, grid, 512, smem, st, a);
+    if (!attr512) { B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 17)); attr512 = true; }
+    B2_LAUNCH(ctx, (ntt_pass<512, 1>), grid, 512, smem, st, a);
   } else {
-    static bool attr256 = false;
-    if (!attr256) { B2_CUDA(ctx, cudaFuncSetAttribute(ntt_pass<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16)); attr256 = true; }
-    B2_LAUNCH(ctx, ntt_pass<256>, grid, 256, smem, st, a);
+    // 64 KiB tiles: three CTAs fit an SM's shared memory; MINB = 3 caps registers at 85 so that they also fit
+    // its register file (experiment knob B200ZK_NTT_MINB=2 keeps the uncapped 100-register build)
+    static int minb = 0;
+    if (!minb) {
+      const char* e = getenv("B200ZK_NTT_MINB");
+      minb = (e && *e == '2') ? 2 : 3;
+      B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<256, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16));
+      B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<256, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16));
+    }
+    if (minb == 2) B2_LAUNCH(ctx, (ntt_pass<256, 2>), grid, 256, smem, st, a);
+    else B2_LAUNCH(ctx, (ntt_pass<256, 3>), grid, 256, smem, st, a);
   }
   return B200ZK_OK;
 }
@@ -334,7 +381,8 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
     B2_CUDA(ctx, cudaStreamSynchronize(st));  // h is a stack buffer
     c_lo = base + 64; c_hi = base + 64 + (size_t)n_lo * 32;
     B2_LAUNCH(ctx, ntt_build_pow_tables, (n_lo + n_hi + 127) / 128, 128, 0, st, (const uint32_t*)base, inverse ? 1 : 0, inverse ? 1 : 0, log_n, c_lo, n_lo, c_hi, n_hi);
-    if (!inverse) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, log_n > (uint32_t)kLoBits ? 1 : 0);
+    // log_n == 0 has no pass to fuse into: scale the single element directly
+    if (!inverse && log_n == 0) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, 0);
   }
 
   if (log_n > 0) {
@@ -351,6 +399,9 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
       a.out = pl.P == 1 ? d_data : bufs[cur ^ 1];
       a.log_n = log_n; a.s = pl.s[p]; a.t = pl.t[p]; a.log_ns = log_ns;
       a.scale_out = (inverse && !coset && p == pl.P - 1) ? 1 : 0;
+      a.coset_in = (coset && !inverse && p == 0) ? 1 : 0;
+      a.coset_out = (coset && inverse && p == pl.P - 1) ? 1 : 0;
+      a.c_lo = (const uint4*)c_lo; a.c_hi = (const uint4*)c_hi;
       a.tb = tb;
       B2_TRY(launch_pass(ctx, a, st));
       log_ns += pl.s[p];
@@ -358,7 +409,7 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
     }
     if (pl.P > 1 && cur == 1) B2_CUDA(ctx, cudaMemcpyAsync(d_data, ctx->ws_ntt.p, n * 32, cudaMemcpyDeviceToDevice, st));
   }
-  if (coset && inverse) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, log_n > (uint32_t)kLoBits ? 1 : 0);
+  if (coset && inverse && log_n == 0) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, 0);
   if (canonical) B2_LAUNCH(ctx, fr_convert, egrid, 256, 0, st, d_data, n, 0, be ? 1 : 0);
   return B200ZK_OK;
 }
