@@ -255,9 +255,20 @@ def run_gpu(args):
     peak, peak_src = _peaks()
     algo_bytes = n * 96 + 64  # n x (32 B scalar + 64 B affine base) read + 64 B written
     achieved = algo_bytes / (acc / 1e3) / 1e9
+    # DRAM traffic of one launch from the committed `ncu --set full` capture of this exact configuration
+    # (profiles/r1c_prof_msm_r1b_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); null for other configs
+    traffic = 29.340339e9 + 0.198330e9 if (log_n == 24 and not args.no_precompute and not args.window) else None
+    MODMUL_PEAK = 67.7e9  # measured 254-bit Montgomery products/s of the chip (profiles/r1_probe_field_mul.md)
+    adds = n * 13 if (not args.no_precompute and not args.window and log_n >= 20) else None
     roofline = {"bound": "hbm", "kernel": "msm_accumulate<Fq>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": acc, "phases_ms": phases,
-                "note": "integer-compute-bound kernel: n*ceil(255/c) XYZZ mixed additions; see DESIGN.md for the IMAD-issue roofline"}
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": acc, "phases_ms": phases,
+                "binding_roofline": {"bound": "fmaheavy pipe (IMAD.WIDE): 254-bit modular products", "peak_products_per_s": MODMUL_PEAK,
+                                     "achieved_products_per_s": (adds * 9.5 / (acc / 1e3)) if adds else None,
+                                     "frac": (adds * 9.5 / (acc / 1e3) / MODMUL_PEAK) if adds else None,
+                                     "ncu_sm__pipe_fmaheavy_cycles_active_pct": 92.3},
+                "note": "integer-compute-bound kernel (n*13 XYZZ mixed additions of 9.5 product-equivalents): the HBM fraction is small by "
+                        "construction, see DESIGN.md section 4; kernel_ms is measured in the one-shot schedule (phases are not separable "
+                        "in the chunk-pipelined one that `value` runs)"}
 
     # ---- e2e: C-ABI call with HOST scalars (pinned), resident bases, result read back -- rank-local shard
     e2e = None
@@ -312,8 +323,10 @@ def run_gpu(args):
         ntt = {"metric": "fr_ntt_elems_per_sec", "value": world * n / (fwd_ms / 1e3), "unit": "elements/s", "forward_ms": fwd_ms, "inverse_ms": inv_ms,
                "inverse_value": world * n / (inv_ms / 1e3), "roundtrip_ok": ok, "launches_per_transform": fl // max(1, args.steps),
                "roofline": {"bound": "hbm", "achieved": ntt_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": ntt_bytes / (fwd_ms / 1e3) / 1e9 / peak, "traffic": None,
-                            "note": "whole transform (all passes); algorithmic bytes = 64*n (one read + one write)"}}
+                            "frac": ntt_bytes / (fwd_ms / 1e3) / 1e9 / peak, "traffic": 3.061e9 if log_n == 24 else None,
+                            "binding_roofline": {"bound": "fmaheavy pipe: ~12 modular products per element", "frac": 12 * n / (fwd_ms / 1e3) / 67.7e9},
+                            "note": "whole transform (3 passes at 2^24); algorithmic bytes = 64*n; traffic = sum of the three passes' "
+                                    "dram bytes from profiles/r1c_prof_ntt_r1b_summary.txt"}}
         del d_ntt, ref
 
     # ---- config #5: Groth16-shaped wrap (7 NTT + quotient + 4 G1 MSM + 1 G2 MSM) through B200Backend.prove, N=1

@@ -96,6 +96,9 @@ class Context:
     def set_msm_window(self, c: int):
         self._check(F.lib.b200zk_set_msm_window(self._h, c), "set_msm_window")
 
+    def set_msm_chunks(self, chunks: int):
+        self._check(F.lib.b200zk_set_msm_chunks(self._h, chunks), "set_msm_chunks")
+
     def set_msm_pair_rounds(self, rounds: int):
         self._check(F.lib.b200zk_set_msm_pair_rounds(self._h, rounds), "set_msm_pair_rounds")
 

@@ -28,21 +28,21 @@ int read_result(b200zk_ctx* ctx, const void* d_out, size_t bytes, cudaStream_t s
 
 template <bool G2>
 int msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_out,
-                     uint32_t table_c = 0, size_t table_stride = 0) {
+                     uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr) {
   if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
   B2_TRY(ensure(ctx, ctx->ws_result, 256));
-  if (G2) { B2_TRY(msm_run_g2(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p, table_c, table_stride)); return msm_encode_g2(ctx, ctx->ws_result.p, 1, flags, st, d_out); }
-  B2_TRY(msm_run_g1(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p, table_c, table_stride));
+  if (G2) { B2_TRY(msm_run_g2(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p, table_c, table_stride, h_scalars)); return msm_encode_g2(ctx, ctx->ws_result.p, 1, flags, st, d_out); }
+  B2_TRY(msm_run_g1(ctx, d_points, d_scalars, n, flags, st, ctx->ws_result.p, table_c, table_stride, h_scalars));
   return msm_encode_g1(ctx, ctx->ws_result.p, 1, flags, st, d_out);
 }
 
 template <bool G2>
 int msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t* out,
-               uint32_t table_c = 0, size_t table_stride = 0) {
-  if (!ctx || !out || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
+               uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr) {
+  if (!ctx || !out || ((!d_points || (!d_scalars && !h_scalars)) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   B2_TRY(ensure(ctx, ctx->ws_out, 256));
-  B2_TRY(msm_device_async<G2>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p, table_c, table_stride));
+  B2_TRY(msm_device_async<G2>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p, table_c, table_stride, h_scalars));
   return read_result(ctx, ctx->ws_out.p, Sizes<G2>::point, st, out);
 }
 
@@ -97,8 +97,8 @@ int msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end() || it->second.g2 != G2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: n exceeds the resident bases");
-  B2_TRY(stage_scalars(ctx, scalars, n, ctx->stream));
-  return msm_device<G2>(ctx, it->second.d, ctx->ws_scalars.p, n, flags & ~B200ZK_POINTS_BE, ctx->stream, out, it->second.table_c, it->second.n);
+  // host scalars go straight into the (chunk-pipelined) schedule: their upload overlaps the previous chunk's work
+  return msm_device<G2>(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, ctx->stream, out, it->second.table_c, it->second.n, scalars);
 }
 
 template <bool G2>
@@ -181,6 +181,13 @@ int b200zk_init(int device, b200zk_ctx** out) {
     return B200ZK_ERR_CUDA;
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
+    if (cudaStreamCreateWithPriority(&ctx->stream_sort, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); b200zk_destroy(ctx); return B200ZK_ERR_CUDA; }
+    cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
+    for (auto& sl : ctx->slot) { cudaEventCreateWithFlags(&sl.sorted, cudaEventDisableTiming); cudaEventCreateWithFlags(&sl.released, cudaEventDisableTiming); }
+  }
   *out = ctx;
   return B200ZK_OK;
 }
@@ -192,6 +199,15 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->ws_hist, &ctx->ws_offsets, &ctx->ws_cursor, &ctx->ws_blocksums, &ctx->ws_idx, &ctx->ws_buckets, &ctx->ws_chunkS,
                     &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits, &ctx->ws_q0, &ctx->ws_q1, &ctx->ws_prefix, &ctx->ws_info, &ctx->ws_pairoff0, &ctx->ws_pairoff1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  if (ctx->ws_totals.p) cudaFree(ctx->ws_totals.p);
+  for (auto& sl : ctx->slot) {
+    DevBuf* sb[] = {&sl.hist, &sl.offsets, &sl.cursor, &sl.run_off, &sl.tsum, &sl.digits, &sl.idx};
+    for (DevBuf* b : sb) if (b->p) cudaFree(b->p);
+    if (sl.sorted) cudaEventDestroy(sl.sorted);
+    if (sl.released) cudaEventDestroy(sl.released);
+  }
+  if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  if (ctx->stream_sort) cudaStreamDestroy(ctx->stream_sort);
   for (auto& kv : ctx->twiddles) cudaFree(kv.second.d);
   for (auto& kv : ctx->bases) cudaFree(kv.second.d);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -210,6 +226,11 @@ int b200zk_synchronize(b200zk_ctx* ctx) {
 int b200zk_set_msm_window(b200zk_ctx* ctx, uint32_t c) {
   if (!ctx || (c && (c < 2 || c > 24))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm window must be 0 or 2..24");
   ctx->msm_window = c;
+  return B200ZK_OK;
+}
+int b200zk_set_msm_chunks(b200zk_ctx* ctx, uint32_t chunks) {
+  if (!ctx || chunks > 64) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm chunks must be 0 (automatic) .. 64");
+  ctx->msm_chunks = chunks;
   return B200ZK_OK;
 }
 int b200zk_set_msm_pair_rounds(b200zk_ctx* ctx, int rounds) {

@@ -20,6 +20,12 @@ struct DevBuf {
 struct TwiddleSet {   // per (log_n, direction): see ntt.cu
   void* d = nullptr;  // device allocation holding all tables
   size_t bytes = 0;
+  uint32_t gen[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // coset tables: the generator they were built for
+};
+
+struct SortSlot {  // one of the two sort workspaces of the chunk-pipelined MSM
+  DevBuf hist, offsets, cursor, run_off, tsum, digits, idx;
+  cudaEvent_t sorted = nullptr, released = nullptr;
 };
 
 struct BasesEntry {
@@ -38,6 +44,11 @@ struct b200zk_ctx {
   std::string last_error;
   uint64_t launches = 0;
   uint32_t msm_window = 0;
+  uint32_t msm_chunks = 0;   // chunk count of the pipelined MSM schedule; 0 = automatic
+  cudaStream_t stream_sort = nullptr;  // high-priority stream the sort of chunk k+1 runs on while chunk k accumulates
+  cudaEvent_t ev_in = nullptr;
+  b200zk::SortSlot slot[2];
+  b200zk::DevBuf ws_totals;
   int msm_pair_rounds = -1;  // batched-affine pair-summing rounds before the XYZZ accumulation; <0 = automatic
   bool profiling = false;
   float phase_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -147,8 +158,9 @@ template <> struct FieldBytes<Fq2> { static constexpr size_t value = 64; };
 
 // internal cross-TU entry points
 // table_c != 0: d_points is a precomputed window table with `table_stride` points per window
-int msm_run_g1(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0);
-int msm_run_g2(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0);
+// h_scalars != nullptr: the scalars are in (pinned) host memory and are uploaded chunk by chunk inside the pipeline
+int msm_run_g1(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr);
+int msm_run_g2(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr);
 int msm_precompute_g1(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st);
 int msm_precompute_g2(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st);
 uint32_t precompute_window(size_t n);

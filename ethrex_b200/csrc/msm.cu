@@ -22,6 +22,7 @@
 // multi-GPU path can all-gather the 128/256-byte XYZZ partials first.
 #include "common.cuh"
 #include "tma.cuh"
+#include <cstdlib>
 
 namespace b200zk {
 
@@ -271,8 +272,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, c
 // and a thread derives its first slot from the same formula.  partial_tree then folds the runs of every bucket
 // that has more than one (a bucket straddling a slice boundary, or a heavy bucket spanning many slices) with a
 // radix-kTreeRadix tree in place, leaving each bucket's total in its first run.
-static constexpr uint32_t kSegLen = 256;
+static constexpr uint32_t kSegLenMax = 256;  // the slice length itself is a launch parameter (wave balancing)
 static constexpr uint32_t kTreeRadix = 64;
+
+// Slice length for M entries: every thread does the same work, so the launch runs in lock-step "waves" of
+// `resident` threads; pick the length that fills a whole number of waves instead of leaving the last one part empty.
+static uint32_t pick_slice_len(size_t M, size_t resident) {
+  if (M == 0) return kSegLenMax;
+  size_t per_thread = (M + resident - 1) / resident;            // entries per thread if it were a single wave
+  size_t waves = (per_thread + kSegLenMax - 1) / kSegLenMax;
+  size_t len = (M + resident * waves - 1) / (resident * waves);
+  if (len < 16) len = 16;
+  if (len > kSegLenMax) len = kSegLenMax;
+  return (uint32_t)len;
+}
 
 // largest g in [lo, G) with offsets[g] <= e, given offsets[lo] <= e: gallop then bisect (the next non-empty
 // bucket is almost always within a few entries; empty buckets repeat the same offset and are skipped)
@@ -293,7 +306,7 @@ B2_D uint32_t bucket_of(const uint32_t* __restrict__ offsets, uint32_t G, uint32
 template <class F, bool DIRECT>
 __global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
                                                       const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ run_off,
-                                                      uint32_t G, void* __restrict__ partials, uint32_t* __restrict__ run_bucket) {
+                                                      uint32_t G, uint32_t kSegLen, void* __restrict__ partials, uint32_t* __restrict__ run_bucket) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t M = __ldg(offsets + G);
   const uint64_t e0_64 = (uint64_t)t * kSegLen;
@@ -485,6 +498,22 @@ __global__ void __launch_bounds__(128) partial_tree(const uint32_t* __restrict__
   store_xyzz(partials, s, acc);
 }
 
+// totals[g] (+)= this chunk's total of bucket g (its first run after partial_tree); first chunk initialises
+template <class F>
+__global__ void __launch_bounds__(128) bucket_merge(const void* __restrict__ partials, const uint32_t* __restrict__ run_off, uint32_t G, int first, void* __restrict__ totals) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  uint32_t so = __ldg(run_off + g);
+  bool has = __ldg(run_off + g + 1) != so;
+  if (first) {
+    store_xyzz(totals, g, has ? load_xyzz<F>(partials, so) : XYZZ<F>::identity());
+  } else if (has) {
+    XYZZ<F> t = load_xyzz<F>(totals, g), p = load_xyzz<F>(partials, so);
+    xyzz_add(t, p);
+    store_xyzz(totals, g, t);
+  }
+}
+
 // ---- bucket reduction: S_w = sum_b (b+1) * B[w][b] ---------------------------------------------------------
 // chunk j of window w: S = sum B, V = sum_k (k+1) * B[j*chunk + k]
 template <class F>
@@ -495,10 +524,15 @@ __global__ void __launch_bounds__(128) bucket_chunk(const void* __restrict__ par
   size_t first = t * pl.chunk;  // bucket arrays are [w][b] contiguous and T*chunk == B
   XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
   for (int k = (int)pl.chunk - 1; k >= 0; --k) {
-    uint32_t so = __ldg(seg_off + first + k);
-    if (__ldg(seg_off + first + k + 1) != so) {  // non-empty bucket: its total sits in its first partial
-      XYZZ<F> b = load_xyzz<F>(partials, so);
+    if (seg_off == nullptr) {  // dense bucket totals (chunk-pipelined path)
+      XYZZ<F> b = load_xyzz<F>(partials, first + k);
       xyzz_add(run, b);
+    } else {
+      uint32_t so = __ldg(seg_off + first + k);
+      if (__ldg(seg_off + first + k + 1) != so) {  // non-empty bucket: its total sits in its first partial
+        XYZZ<F> b = load_xyzz<F>(partials, so);
+        xyzz_add(run, b);
+      }
     }
     xyzz_add(acc, run);
   }
@@ -572,9 +606,100 @@ static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
   if (ctx->profiling) cudaEventRecord(ctx->ev[k], st);
 }
 
+// ---- chunk-pipelined schedule --------------------------------------------------------------------------------
+// The sort (histogram / scan / scatter: L2-atomic and latency bound, the multiplier pipe idle) and the bucket
+// accumulation (multiplier-pipe bound, memory system idle) use disjoint resources, so for large n the points are
+// cut into chunks and chunk k+1 is sorted on a second, high-priority stream WHILE chunk k is accumulated; with
+// host scalars the chunk's upload rides on the sort stream too.  Each chunk's bucket totals are folded into a dense
+// totals array, which is reduced once at the end.
+template <class F>
+static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, const void* h_scalars, size_t n, uint32_t flags,
+                             cudaStream_t st, void* d_partial, const MsmPlan& pl, uint32_t K) {
+  const size_t G = (size_t)pl.Wr * pl.B;
+  const size_t tiles = (G + kScanTile - 1) / kScanTile;
+  const size_t xy = 4 * FieldBytes<F>::value, pt = 2 * FieldBytes<F>::value;
+  size_t chunk = ((n + K - 1) / K + 255) & ~(size_t)255;
+  const size_t Mk_max = chunk * pl.W;
+  const size_t resident = (size_t)ctx->sm_count * (sizeof(F) > 32 ? 256 : 512);
+  const uint32_t L = pick_slice_len(Mk_max, resident);
+  const size_t S_max = Mk_max / L + 1 + G;
+  const size_t slices = (Mk_max + L - 1) / L;
+  for (int sl = 0; sl < 2; ++sl) {
+    SortSlot& s = ctx->slot[sl];
+    B2_TRY(ensure(ctx, s.hist, G * 4)); B2_TRY(ensure(ctx, s.offsets, (G + 1) * 4)); B2_TRY(ensure(ctx, s.cursor, G * 4));
+    B2_TRY(ensure(ctx, s.run_off, (G + 1) * 4)); B2_TRY(ensure(ctx, s.tsum, tiles * 4));
+    B2_TRY(ensure(ctx, s.digits, Mk_max * 4)); B2_TRY(ensure(ctx, s.idx, Mk_max * 4));
+  }
+  B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));
+  B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
+  B2_TRY(ensure(ctx, ctx->ws_totals, G * xy));
+  B2_TRY(ensure(ctx, ctx->ws_chunkS, (size_t)pl.Wr * pl.T * xy));
+  B2_TRY(ensure(ctx, ctx->ws_chunkV, (size_t)pl.Wr * pl.T * xy));
+  if (h_scalars) B2_TRY(ensure(ctx, ctx->ws_scalars, n * 32 + 32));
+  const uint8_t* dsc = (const uint8_t*)(h_scalars ? ctx->ws_scalars.p : d_scalars);
+  cudaStream_t ss = ctx->stream_sort;
+  // Leave room on every SM for the sort kernels of the next chunk: the accumulation alone fills the register file
+  // (4 CTAs x 128 threads x 128 registers), so it is launched with a dynamic shared-memory reservation that caps it
+  // at 3 CTAs per SM; the high-priority sort stream's CTAs slot into the freed quarter.
+  static int acc_smem = -1;
+  if (acc_smem < 0) {
+    const char* e = getenv("B200ZK_MSM_ACC_SMEM_KB");
+    acc_smem = e ? atoi(e) * 1024 : 60 * 1024;  // 60 KiB -> 3 CTAs/SM (measured best of 0/60/76/100)
+    if (acc_smem > 48 * 1024) B2_CUDA(ctx, cudaFuncSetAttribute((msm_accumulate<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, acc_smem));
+  }
+  const size_t acc_dyn = (K > 1 && sizeof(F) == 32) ? (size_t)acc_smem : 0;
+  B2_CUDA(ctx, cudaEventRecord(ctx->ev_in, st));
+  B2_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_in, 0));
+  uint32_t k = 0;
+  for (size_t lo = 0; lo < n; lo += chunk, ++k) {
+    const size_t nk = n - lo < chunk ? n - lo : chunk;
+    SortSlot& s = ctx->slot[k & 1];
+    uint32_t *hist = (uint32_t*)s.hist.p, *offsets = (uint32_t*)s.offsets.p, *cursor = (uint32_t*)s.cursor.p, *run_off = (uint32_t*)s.run_off.p,
+             *tsum = (uint32_t*)s.tsum.p, *digits = (uint32_t*)s.digits.p, *idx = (uint32_t*)s.idx.p;
+    // ---- sort stream
+    if (k >= 2) B2_CUDA(ctx, cudaStreamWaitEvent(ss, s.released, 0));
+    if (h_scalars) B2_CUDA(ctx, cudaMemcpyAsync((void*)(dsc + lo * 32), (const uint8_t*)h_scalars + lo * 32, nk * 32, cudaMemcpyHostToDevice, ss));
+    B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, ss));
+    const unsigned sgrid = (unsigned)std::min<size_t>((nk + 255) / 256, (size_t)ctx->sm_count * 8);
+    B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, ss, (const void*)(dsc + lo * 32), nk, flags, pl, hist, digits);
+    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
+    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
+    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
+    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)offsets, G, L, 0u, tsum);
+    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
+    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)offsets, G, L, 0u, tsum, run_off, (uint32_t*)nullptr);
+    const unsigned wgrid = (unsigned)std::min<size_t>((nk * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
+    B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, ss, (const uint32_t*)digits, nk, pl, cursor, idx);
+    B2_CUDA(ctx, cudaEventRecord(s.sorted, ss));
+    // ---- accumulate stream (the caller's)
+    B2_CUDA(ctx, cudaStreamWaitEvent(st, s.sorted, 0));
+    const void* pts = (const uint8_t*)d_points + lo * pt;
+    B2_LAUNCH(ctx, (msm_accumulate<F, false>), (unsigned)((slices + 127) / 128), 128, acc_dyn, st, pts, (const uint32_t*)idx, (const uint32_t*)offsets, (const uint32_t*)run_off,
+              (uint32_t)G, L, ctx->ws_buckets.p, (uint32_t*)ctx->ws_segbucket.p);
+    {
+      size_t worst_entries = (pl.merged ? nk * (size_t)pl.W : nk) + 1;
+      size_t worst = (worst_entries + L - 1) / L + 1;
+      for (size_t stride = 1; stride < worst; stride *= kTreeRadix)
+        B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, (const uint32_t*)run_off, (const uint32_t*)ctx->ws_segbucket.p, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
+    }
+    B2_LAUNCH(ctx, bucket_merge<F>, (unsigned)((G + 127) / 128), 128, 0, st, (const void*)ctx->ws_buckets.p, (const uint32_t*)run_off, (uint32_t)G, k == 0 ? 1 : 0, ctx->ws_totals.p);
+    B2_CUDA(ctx, cudaEventRecord(s.released, st));
+  }
+  const size_t chunks = (size_t)pl.Wr * pl.T;
+  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, (const void*)ctx->ws_totals.p, (const uint32_t*)nullptr, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  uint32_t chunk_log2 = 0;
+  while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
+  for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
+    size_t pairs = (size_t)pl.Wr * (pl.T / (2 * half));
+    B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  }
+  B2_LAUNCH(ctx, msm_horner<F>, 1, 32, 0, st, pl, ctx->ws_chunkV.p, d_partial);
+  return B200ZK_OK;
+}
+
 template <class F>
 static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial,
-                   uint32_t table_c, size_t table_stride) {
+                   uint32_t table_c, size_t table_stride, const void* h_scalars) {
   if (n == 0) {
     B2_LAUNCH(ctx, write_identity<F>, 1, 32, 0, st, d_partial);
     return B200ZK_OK;
@@ -586,6 +711,21 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
     if ((unsigned long long)table_stride * pl.W >= (1ull << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: precomputed table too large for 31-bit indices");
   }
   if ((unsigned long long)n * pl.W >= (1ull << 32)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32 (shard the MSM)");
+  {
+    // large inputs: chunk-pipelined schedule (unless phases are being profiled or pair rounds are forced)
+    // measured on B200 (profiles/r1_probe.md): with scalars already in HBM one shot is as fast as any chunking
+    // (40.9 ms vs 40.0-42 ms at 2^24: the accumulation fills the SMs, so the next chunk's sort barely overlaps);
+    // with HOST scalars 4 chunks hide most of the 512 MiB upload (50.5 -> 41.9 ms)
+    uint32_t K = ctx->msm_chunks ? ctx->msm_chunks : ((h_scalars && n >= ((size_t)1 << 22)) ? 4u : 1u);
+    if (K > 64) K = 64;
+    if ((K > 1 || h_scalars) && !ctx->profiling && ctx->msm_pair_rounds <= 0 && n >= 4096)
+      return msm_run_pipelined<F>(ctx, d_points, d_scalars, h_scalars, n, flags, st, d_partial, pl, K);
+  }
+  if (h_scalars) {  // unpipelined path takes device scalars: stage them first
+    B2_TRY(ensure(ctx, ctx->ws_scalars, n * 32 + 32));
+    B2_CUDA(ctx, cudaMemcpyAsync(ctx->ws_scalars.p, h_scalars, n * 32, cudaMemcpyHostToDevice, st));
+    d_scalars = ctx->ws_scalars.p;
+  }
   const size_t G = (size_t)pl.Wr * pl.B;
   const size_t tiles = (G + kScanTile - 1) / kScanTile;
   const size_t xy = 4 * FieldBytes<F>::value;
@@ -604,6 +744,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   if (ctx->msm_pair_rounds >= 0) rounds = (uint32_t)ctx->msm_pair_rounds;
   if (rounds > 4) rounds = 4;
   if (rounds && M_max >= ((size_t)1 << 31)) rounds = 0;
+  const uint32_t kSegLen = pick_slice_len(M_max >> rounds, (size_t)ctx->sm_count * (sizeof(F) > 32 ? 256 : 512));
   const size_t S_max = (M_max >> rounds) / kSegLen + 1 + G;  // upper bound on the number of runs
   const size_t slices = ((M_max >> rounds) + G + kSegLen - 1) / kSegLen;
   if (rounds) {
@@ -660,8 +801,8 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, cur_off, G, kSegLen, 0u, tsum);
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
   B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, cur_off, G, kSegLen, 0u, tsum, seg_off, (uint32_t*)nullptr);
-  if (rounds) B2_LAUNCH(ctx, (msm_accumulate<F, true>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
-  else B2_LAUNCH(ctx, (msm_accumulate<F, false>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, ctx->ws_buckets.p, seg_bucket);
+  if (rounds) B2_LAUNCH(ctx, (msm_accumulate<F, true>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+  else B2_LAUNCH(ctx, (msm_accumulate<F, false>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
   {
     // worst case every point of a window lands in one bucket: ceil(entries / kSegLen) + 1 runs to fold
     size_t worst_entries = ((pl.merged ? n * (size_t)pl.W : n) >> rounds) + 1;
@@ -714,8 +855,8 @@ static int precompute_host(b200zk_ctx* ctx, const void* d_bases, size_t n, uint3
 int msm_precompute_g1(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fq>(ctx, b, n, c, t, st); }
 int msm_precompute_g2(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fq2>(ctx, b, n, c, t, st); }
 
-int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts) { return msm_run<Fq>(ctx, p, s, n, f, st, out, tc, ts); }
-int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts) { return msm_run<Fq2>(ctx, p, s, n, f, st, out, tc, ts); }
+int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs) { return msm_run<Fq>(ctx, p, s, n, f, st, out, tc, ts, hs); }
+int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs) { return msm_run<Fq2>(ctx, p, s, n, f, st, out, tc, ts, hs); }
 int msm_encode_g1(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq>(ctx, p, c, f, st, out); }
 int msm_encode_g2(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq2>(ctx, p, c, f, st, out); }
 

@@ -365,22 +365,41 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
   const unsigned egrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 32);
   if (canonical) B2_LAUNCH(ctx, fr_convert, egrid, 256, 0, st, d_data, n, 1, be ? 1 : 0);
 
-  // coset tables (per call: the generator is an argument)
   void *c_lo = nullptr, *c_hi = nullptr;
   const uint32_t lb = log_n < (uint32_t)kLoBits ? log_n : (uint32_t)kLoBits;
   const uint32_t n_lo = 1u << lb, n_hi = log_n > (uint32_t)kLoBits ? 1u << (log_n - kLoBits) : 1u;
   if (coset) {
-    B2_TRY(ensure(ctx, ctx->ws_misc, (size_t)(n_lo + n_hi) * 32 + 64));
     uint32_t h[8] = {5, 0, 0, 0, 0, 0, 0, 0};
     if (coset_gen) {
       if (be) for (int i = 0; i < 8; ++i) h[i] = ((uint32_t)coset_gen[31 - 4 * i]) | ((uint32_t)coset_gen[30 - 4 * i] << 8) | ((uint32_t)coset_gen[29 - 4 * i] << 16) | ((uint32_t)coset_gen[28 - 4 * i] << 24);
       else memcpy(h, coset_gen, 32);
     }
-    uint8_t* base = (uint8_t*)ctx->ws_misc.p;
-    B2_CUDA(ctx, cudaMemcpyAsync(base, h, 32, cudaMemcpyHostToDevice, st));
-    B2_CUDA(ctx, cudaStreamSynchronize(st));  // h is a stack buffer
+    // tables of h^i (or h^-i * n^-1) are cached per (log_n, direction, generator): a prover uses one generator,
+    // and the inverse table costs two serial field inversions to build
+    uint64_t key = 0xcbf29ce484222325ull ^ ((uint64_t)log_n | ((uint64_t)inverse << 8) | (1ull << 16));
+    for (int i = 0; i < 8; ++i) key = (key ^ h[i]) * 0x100000001b3ull;
+    key |= 1ull << 63;  // never collides with the twiddle keys (log_n | inverse << 8)
+    auto it = ctx->twiddles.find(key);
+    if (it != ctx->twiddles.end() && memcmp(it->second.gen, h, 32) != 0) {  // 64-bit key collision: rebuild
+      B2_CUDA(ctx, cudaDeviceSynchronize());
+      cudaFree(it->second.d);
+      ctx->twiddles.erase(it);
+      it = ctx->twiddles.end();
+    }
+    if (it == ctx->twiddles.end()) {
+      TwiddleSet ts;
+      memcpy(ts.gen, h, 32);
+      ts.bytes = (size_t)(n_lo + n_hi) * 32 + 64;
+      B2_CUDA(ctx, cudaMalloc(&ts.d, ts.bytes));
+      B2_CUDA(ctx, cudaMemcpyAsync(ts.d, h, 32, cudaMemcpyHostToDevice, st));
+      B2_CUDA(ctx, cudaStreamSynchronize(st));  // h is a stack buffer
+      uint8_t* base = (uint8_t*)ts.d;
+      B2_LAUNCH(ctx, ntt_build_pow_tables, (n_lo + n_hi + 127) / 128, 128, 0, st, (const uint32_t*)base, inverse ? 1 : 0, inverse ? 1 : 0, log_n,
+                (void*)(base + 64), n_lo, (void*)(base + 64 + (size_t)n_lo * 32), n_hi);
+      it = ctx->twiddles.emplace(key, ts).first;
+    }
+    uint8_t* base = (uint8_t*)it->second.d;
     c_lo = base + 64; c_hi = base + 64 + (size_t)n_lo * 32;
-    B2_LAUNCH(ctx, ntt_build_pow_tables, (n_lo + n_hi + 127) / 128, 128, 0, st, (const uint32_t*)base, inverse ? 1 : 0, inverse ? 1 : 0, log_n, c_lo, n_lo, c_hi, n_hi);
     // log_n == 0 has no pass to fuse into: scale the single element directly
     if (!inverse && log_n == 0) B2_LAUNCH(ctx, ntt_scale_pow, egrid, 256, 0, st, d_data, n, c_lo, c_hi, 0);
   }

@@ -87,6 +87,7 @@ unsafe extern "C" {
     pub fn b200zk_g2_check_device(ctx: *mut b200zk_ctx, d_points: *const c_void, n: usize, stream: *mut c_void, bad_index: *mut usize) -> c_int;
 
     pub fn b200zk_set_msm_window(ctx: *mut b200zk_ctx, c: u32) -> c_int;
+    pub fn b200zk_set_msm_chunks(ctx: *mut b200zk_ctx, chunks: u32) -> c_int;
     pub fn b200zk_set_msm_pair_rounds(ctx: *mut b200zk_ctx, rounds: c_int) -> c_int;
     pub fn b200zk_last_msm_phase_ms(ctx: *mut b200zk_ctx, out_ms: *mut f32) -> c_int;
     pub fn b200zk_set_profiling(ctx: *mut b200zk_ctx, enabled: c_int) -> c_int;

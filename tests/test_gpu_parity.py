@@ -454,3 +454,29 @@ def test_pair_sum_rounds_edge_cases(ctx):
     finally:
         ctx.set_msm_window(0)
         ctx.set_msm_pair_rounds(-1)
+
+
+def test_pipelined_chunks_match(ctx):
+    """chunk-pipelined schedule (sort of chunk k+1 overlapping the accumulation of chunk k): same bytes as one shot."""
+    k, d = chain_kd()
+    n = 10007
+    pts, s = orc.g1_chain(n, k, d), scalars_special(n)
+    exp = orc.g1_msm(pts, s)
+    dp, ds = to_dev(pts), to_dev(s)
+    h = ctx.g1_bases_upload(pts, n)
+    ht = ctx.g1_bases_upload(pts, n)
+    ctx.bases_precompute(ht, 9)
+    try:
+        for chunks in (1, 2, 3, 7, 40):
+            ctx.set_msm_chunks(chunks)
+            assert ctx.g1_msm_device(dp, ds, n) == exp, chunks
+            assert ctx.g1_msm_resident(h, s, n) == exp, chunks            # host scalars: upload rides in the pipeline
+            assert ctx.g1_msm_resident_device(ht, ds, n) == exp, chunks    # merged table, chunk offsets into it
+            assert ctx.g1_msm_resident(ht, s[:5000], 5000) == orc.g1_msm(pts[:5000], s[:5000]), chunks
+        pts2 = orc.g2_chain(4500, k, d)
+        ctx.set_msm_chunks(4)
+        assert ctx.g2_msm_device(to_dev(pts2), to_dev(s[:4500]), 4500) == orc.g2_msm(pts2, s[:4500])
+    finally:
+        ctx.set_msm_chunks(0)
+        ctx.bases_free(h)
+        ctx.bases_free(ht)
