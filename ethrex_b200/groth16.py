@@ -47,17 +47,23 @@ class SyntheticWrapCircuit:
     """Domain size 2^log_n; `n` witness entries; H has n-1 coefficients."""
     QUERIES = (("a_g1", False), ("b_g1", False), ("b_g2", True), ("l_g1", False), ("h_g1", False))
 
-    def __init__(self, ctx, log_n: int, precompute: bool = True, g2: bool = True):
+    def __init__(self, ctx, log_n: int, precompute: bool = True, g2: bool = True, rank: int = 0, world: int = 1):
+        """rank/world: every rank keeps only its contiguous shard [lo, hi) of each proving-key column (point-split
+        MSMs, ethrex_b200.dist.msm_sharded); the NTTs of the quotient are cheap and computed on every rank."""
         import torch
+        from .dist import shard_range
         self.ctx, self.log_n, self.n = ctx, log_n, 1 << log_n
+        self.rank, self.world = rank, world
+        self.lo, self.hi = shard_range(self.n, rank, world)
         self.pk = ProvingKey(log_n)
+        m = self.hi - self.lo
         for name, is_g2 in self.QUERIES:
             if is_g2 and not g2:
                 continue
             k, d = _chain_kd(name.encode())
-            pts = torch.empty((16 if is_g2 else 8) * self.n, dtype=torch.int64, device="cuda")
-            (ctx.g2_chain_device if is_g2 else ctx.g1_chain_device)(pts, 0, self.n, k, d)
-            h = (ctx.g2_bases_from_device if is_g2 else ctx.g1_bases_from_device)(pts, self.n)
+            pts = torch.empty((16 if is_g2 else 8) * m, dtype=torch.int64, device="cuda")
+            (ctx.g2_chain_device if is_g2 else ctx.g1_chain_device)(pts, self.lo, m, k, d)
+            h = (ctx.g2_bases_from_device if is_g2 else ctx.g1_bases_from_device)(pts, m)
             del pts
             if precompute:
                 ctx.bases_precompute(h, 0)
@@ -103,7 +109,13 @@ class SyntheticWrapCircuit:
 
         def local(name, scalars, count, flags):
             hnd = self.pk.handles[name]
-            if self.pk.chains[name][2]:
+            is_g2 = self.pk.chains[name][2]
+            if self.world > 1:  # this rank's slice of the scalars against its shard of the column, then all-gather + fold
+                from .dist import msm_sharded
+                hi = min(self.hi, count)
+                m = max(0, hi - self.lo)
+                return msm_sharded(ctx, None, scalars[4 * self.lo: 4 * (self.lo + max(m, 1))], m, flags, g2=is_g2, handle=hnd)
+            if is_g2:
                 return ctx.g2_msm_resident_device(hnd, scalars, count, flags)
             return ctx.g1_msm_resident_device(hnd, scalars, count, flags)
 

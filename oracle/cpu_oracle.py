@@ -220,3 +220,13 @@ def fr_ntt(data_mont: np.ndarray, log_n: int, flags: int = 0, coset_gen: int | N
     if rc:
         raise ValueError(f"ntt status {rc}")
     return a
+
+
+def fr_ntt_eval_output(data_mont: np.ndarray, log_n: int, k: int) -> np.ndarray:
+    """output k of the forward NTT by direct evaluation (O(n)); Montgomery limbs in and out."""
+    a = np.ascontiguousarray(data_mont)
+    out = np.empty(4, dtype=np.uint64)
+    rc = lib().orc_fr_ntt_eval_output(_p(a), C.c_uint(log_n), C.c_uint64(k), _p(out))
+    if rc:
+        raise ValueError(f"ntt eval status {rc}")
+    return out

@@ -480,3 +480,19 @@ def test_pipelined_chunks_match(ctx):
         ctx.set_msm_chunks(0)
         ctx.bases_free(h)
         ctx.bases_free(ht)
+
+
+def test_ntt_2_26_roundtrip_and_direct_evaluation(ctx):
+    """beyond the oracle's reach in full: round trip + a few outputs against the O(n) definition (config #3 property check)."""
+    import torch
+    log_n, n = 26, 1 << 26
+    d = dev_empty(4 * n)
+    ctx.fr_random_device(d, n, pyref.SEED_NTT, 12345, eb.SCALARS_MONT)
+    orig = d.clone()
+    ctx.fr_ntt_device(d, log_n, 0)
+    host_in = to_host(orig).reshape(n, 4)
+    out = to_host(d).reshape(n, 4)
+    for kk in (0, 1, (1 << 25) + 12345, n - 1):
+        assert (orc.fr_ntt_eval_output(host_in, log_n, kk) == out[kk]).all(), kk
+    ctx.fr_ntt_device(d, log_n, eb.NTT_INVERSE)
+    assert torch.equal(d, orig)

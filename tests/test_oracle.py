@@ -133,3 +133,13 @@ def test_msm_properties():
     for vals in ([0] * 64, [1] * 64, [o.R - 1] * 64, [o.R + 3] * 64, [(1 << 256) - 1] * 64):
         sc = orc.ints_to_array(vals)
         assert orc.g1_msm(pts[:64], sc, 0) == orc.g1_msm(pts[:64], sc, 1)
+
+
+def test_ntt_eval_output_is_the_definition():
+    a = orc.fr_to_mont(orc.rand_fr(5, 0, 1 << 10))
+    f = orc.fr_ntt(a, 10)
+    for k in (0, 1, 513, 1023):
+        assert (orc.fr_ntt_eval_output(a, 10, k) == f[k]).all()
+    ai = orc.array_to_ints(orc.fr_from_mont(a))
+    w = o.root_of_unity(10)
+    assert orc.array_to_ints(orc.fr_from_mont(orc.fr_ntt_eval_output(a, 10, 3).reshape(1, 4)))[0] == sum(v * pow(w, 3 * j, o.R) for j, v in enumerate(ai)) % o.R
