@@ -59,6 +59,8 @@ SIGNATURES = {
     "b200zk_g2_msm_partial_device": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g1_msm_partial_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g2_msm_partial_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
+    "b200zk_g1_msm_partial_resident": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
+    "b200zk_g2_msm_partial_resident": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g1_fold_partials_device": (_int, [_ctx, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g2_fold_partials_device": (_int, [_ctx, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_field_to_mont_device": (_int, [_ctx, _vp, _sz, _int, _vp]),

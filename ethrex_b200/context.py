@@ -215,6 +215,14 @@ class Context:
     def g2_msm_partial_resident_device(self, handle: int, d_scalars, n: int, d_partial, flags: int = 0):
         self._check(F.lib.b200zk_g2_msm_partial_resident_device(self._h, handle, _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g2_msm_partial_resident_device")
 
+    def g1_msm_partial_resident(self, handle: int, scalars, n: int, d_partial, flags: int = 0):
+        sp, keep = _host_ptr(scalars)
+        self._check(F.lib.b200zk_g1_msm_partial_resident(self._h, handle, sp, n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g1_msm_partial_resident")
+
+    def g2_msm_partial_resident(self, handle: int, scalars, n: int, d_partial, flags: int = 0):
+        sp, keep = _host_ptr(scalars)
+        self._check(F.lib.b200zk_g2_msm_partial_resident(self._h, handle, sp, n, flags, _current_stream_ptr(), _dev_ptr(d_partial)), "b200zk_g2_msm_partial_resident")
+
     def g1_fold_partials_device(self, d_partials, count: int, flags: int = 0) -> bytes:
         out = C.create_string_buffer(64)
         self._check(F.lib.b200zk_g1_fold_partials_device(self._h, _dev_ptr(d_partials), count, flags, _current_stream_ptr(), out), "b200zk_g1_fold_partials_device")

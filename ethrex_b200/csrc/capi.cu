@@ -200,6 +200,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
                     &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits, &ctx->ws_q0, &ctx->ws_q1, &ctx->ws_prefix, &ctx->ws_info, &ctx->ws_pairoff0, &ctx->ws_pairoff1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->ws_totals.p) cudaFree(ctx->ws_totals.p);
+  if (ctx->ws_bitpart.p) cudaFree(ctx->ws_bitpart.p);
   for (auto& sl : ctx->slot) {
     DevBuf* sb[] = {&sl.hist, &sl.offsets, &sl.cursor, &sl.run_off, &sl.tsum, &sl.digits, &sl.idx};
     for (DevBuf* b : sb) if (b->p) cudaFree(b->p);
@@ -348,6 +349,21 @@ int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, cons
   if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g1(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n);
+}
+// host (pinned) scalars: their upload is chunk-pipelined with the accumulation; the partial stays on the device
+int b200zk_g1_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) {
+  if (!ctx || !d_partial128 || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
+  return msm_run_g1(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n, scalars);
+}
+int b200zk_g2_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
+  if (!ctx || !d_partial256 || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
+  auto it = ctx->bases.find(handle);
+  if (it == ctx->bases.end() || !it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
+  return msm_run_g2(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial256, it->second.table_c, it->second.n, scalars);
 }
 int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
   if (!ctx || !d_partial256 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");

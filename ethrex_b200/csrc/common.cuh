@@ -48,7 +48,7 @@ struct b200zk_ctx {
   cudaStream_t stream_sort = nullptr;  // high-priority stream the sort of chunk k+1 runs on while chunk k accumulates
   cudaEvent_t ev_in = nullptr;
   b200zk::SortSlot slot[2];
-  b200zk::DevBuf ws_totals;
+  b200zk::DevBuf ws_totals, ws_bitpart;
   int msm_pair_rounds = -1;  // batched-affine pair-summing rounds before the XYZZ accumulation; <0 = automatic
   bool profiling = false;
   float phase_ms[6] = {0, 0, 0, 0, 0, 0};

@@ -557,6 +557,59 @@ __global__ void __launch_bounds__(128) bucket_tree(MsmPlan pl, uint32_t half, ui
   store_xyzz(chunkS, left, Sl);
   store_xyzz(chunkV, left, Vl);
 }
+// ---- low-latency combination of the chunk results (replaces the pairwise bucket_tree when T >= 64) ------------
+// Window total = sum_j A_j + chunk * sum_j j * S_j.  The weighted sum is taken bit by bit:
+//   sum_j j * S_j = sum_k 2^k * U_k,   U_k = sum_{j : bit k of j set} S_j
+// so every U_k (and the plain sum of the A_j) is an ordinary, perfectly parallel reduction with no doublings in
+// it; the only serial part left is one Horner over log2(T) + log2(chunk) doublings.  bucket_tree's pairwise
+// merges cost (level + 5) dependent doublings per level, ~90 us each in a lone warp; this is 3 launches.
+static constexpr uint32_t kBitParts = 8;      // blocks per (window, bit): each reduces a slice of the chunks
+static constexpr uint32_t kBitThreads = 128;
+// grid (nbits + 1, Wr, kBitParts); target nbits = plain sum of chunkV
+template <class F>
+__global__ void __launch_bounds__(kBitThreads) bucket_bitsums(MsmPlan pl, uint32_t nbits, const void* __restrict__ chunkS, const void* __restrict__ chunkV, void* __restrict__ partial) {
+  __shared__ uint4 red[kBitThreads * sizeof(XYZZ<F>) / 16];
+  const uint32_t k = blockIdx.x, w = blockIdx.y, part = blockIdx.z;
+  const uint32_t per = pl.T / kBitParts;  // T >= 64 and a power of two
+  XYZZ<F> acc = XYZZ<F>::identity();
+  for (uint32_t j = part * per + threadIdx.x; j < (part + 1) * per; j += kBitThreads) {
+    if (k == nbits) { XYZZ<F> v = load_xyzz<F>(chunkV, (size_t)w * pl.T + j); xyzz_add(acc, v); }
+    else if ((j >> k) & 1) { XYZZ<F> v = load_xyzz<F>(chunkS, (size_t)w * pl.T + j); xyzz_add(acc, v); }
+  }
+  store_xyzz(red, threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t o = kBitThreads / 2; o; o >>= 1) {
+    if (threadIdx.x < o) {
+      XYZZ<F> a = load_xyzz<F>(red, threadIdx.x), b = load_xyzz<F>(red, threadIdx.x + o);
+      xyzz_add(a, b);
+      store_xyzz(red, threadIdx.x, a);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) store_xyzz(partial, ((size_t)w * (nbits + 1) + k) * kBitParts + part, load_xyzz<F>(red, 0));
+}
+// one block per window: thread k folds the kBitParts partials of target k, thread 0 does the Horner and leaves the
+// window total where msm_horner expects it (chunkV[w*T])
+template <class F>
+__global__ void __launch_bounds__(32) bucket_bitfinal(MsmPlan pl, uint32_t nbits, uint32_t chunk_log2, const void* __restrict__ partial, void* __restrict__ chunkV) {
+  __shared__ uint4 u[32 * sizeof(XYZZ<F>) / 16];
+  const uint32_t w = blockIdx.x, k = threadIdx.x;
+  if (k <= nbits) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t part = 0; part < kBitParts; ++part) { XYZZ<F> v = load_xyzz<F>(partial, ((size_t)w * (nbits + 1) + k) * kBitParts + part); xyzz_add(acc, v); }
+    store_xyzz(u, k, acc);
+  }
+  __syncthreads();
+  if (k == 0) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (int b = (int)nbits - 1; b >= 0; --b) { acc = xyzz_dbl(acc); XYZZ<F> v = load_xyzz<F>(u, b); xyzz_add(acc, v); }
+    for (uint32_t i = 0; i < chunk_log2; ++i) acc = xyzz_dbl(acc);
+    XYZZ<F> a = load_xyzz<F>(u, nbits);
+    xyzz_add(acc, a);
+    store_xyzz(chunkV, (size_t)w * pl.T, acc);
+  }
+}
+
 // Horner over the window sums (chunkV[w*T] after the tree): result = sum_w 2^(c*w) * S_w
 template <class F>
 __global__ void msm_horner(MsmPlan pl, const void* __restrict__ chunkV, void* __restrict__ result) {
@@ -689,9 +742,17 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
   B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, (const void*)ctx->ws_totals.p, (const uint32_t*)nullptr, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
   uint32_t chunk_log2 = 0;
   while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
-  for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
-    size_t pairs = (size_t)pl.Wr * (pl.T / (2 * half));
-    B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  if (pl.T >= 64) {
+    uint32_t nbits = 0;
+    while ((1u << nbits) < pl.T) ++nbits;
+    B2_TRY(ensure(ctx, ctx->ws_bitpart, (size_t)pl.Wr * (nbits + 1) * kBitParts * xy));
+    B2_LAUNCH(ctx, bucket_bitsums<F>, dim3(nbits + 1, pl.Wr, kBitParts), kBitThreads, 0, st, pl, nbits, (const void*)ctx->ws_chunkS.p, (const void*)ctx->ws_chunkV.p, ctx->ws_bitpart.p);
+    B2_LAUNCH(ctx, bucket_bitfinal<F>, pl.Wr, 32, 0, st, pl, nbits, chunk_log2, (const void*)ctx->ws_bitpart.p, ctx->ws_chunkV.p);
+  } else {
+    for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
+      size_t pairs = (size_t)pl.Wr * (pl.T / (2 * half));
+      B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+    }
   }
   B2_LAUNCH(ctx, msm_horner<F>, 1, 32, 0, st, pl, ctx->ws_chunkV.p, d_partial);
   return B200ZK_OK;
@@ -815,9 +876,17 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, seg_off, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
   uint32_t chunk_log2 = 0;
   while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
-  for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
-    size_t pairs = (size_t)pl.Wr * (pl.T / (2 * half));
-    B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  if (pl.T >= 64) {
+    uint32_t nbits = 0;
+    while ((1u << nbits) < pl.T) ++nbits;
+    B2_TRY(ensure(ctx, ctx->ws_bitpart, (size_t)pl.Wr * (nbits + 1) * kBitParts * xy));
+    B2_LAUNCH(ctx, bucket_bitsums<F>, dim3(nbits + 1, pl.Wr, kBitParts), kBitThreads, 0, st, pl, nbits, (const void*)ctx->ws_chunkS.p, (const void*)ctx->ws_chunkV.p, ctx->ws_bitpart.p);
+    B2_LAUNCH(ctx, bucket_bitfinal<F>, pl.Wr, 32, 0, st, pl, nbits, chunk_log2, (const void*)ctx->ws_bitpart.p, ctx->ws_chunkV.p);
+  } else {
+    for (uint32_t half = 1, lvl = 0; half < pl.T; half <<= 1, ++lvl) {
+      size_t pairs = (size_t)pl.Wr * (pl.T / (2 * half));
+      B2_LAUNCH(ctx, bucket_tree<F>, (unsigned)((pairs + 127) / 128), 128, 0, st, pl, half, lvl + chunk_log2, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+    }
   }
   phase_mark(ctx, 5, st);
   B2_LAUNCH(ctx, msm_horner<F>, 1, 32, 0, st, pl, ctx->ws_chunkV.p, d_partial);

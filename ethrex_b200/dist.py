@@ -25,8 +25,11 @@ def msm_sharded(ctx, d_points, d_scalars, n_local: int, flags: int = 0, g2: bool
     import torch.distributed as dist
     words = 32 if g2 else 16  # XYZZ partial in int64 words
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    partial = torch.zeros(words, dtype=torch.int64, device=d_scalars.device)
-    if handle is not None:
+    host_scalars = handle is not None and not getattr(d_scalars, "is_cuda", False)
+    partial = torch.zeros(words, dtype=torch.int64, device="cuda" if host_scalars else d_scalars.device)
+    if host_scalars:  # resident bases + pinned host scalars: the upload is pipelined inside the library
+        (ctx.g2_msm_partial_resident if g2 else ctx.g1_msm_partial_resident)(handle, d_scalars, n_local, partial, flags)
+    elif handle is not None:
         (ctx.g2_msm_partial_resident_device if g2 else ctx.g1_msm_partial_resident_device)(handle, d_scalars, n_local, partial, flags)
     else:
         (ctx.g2_msm_partial_device if g2 else ctx.g1_msm_partial_device)(d_points, d_scalars, n_local, partial, flags)

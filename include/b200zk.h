@@ -150,6 +150,11 @@ int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, cons
                                           uint32_t flags, void* stream, void* d_partial128);
 int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n,
                                           uint32_t flags, void* stream, void* d_partial256);
+/* same, with the shard's scalars in (pinned) HOST memory: the upload is pipelined with the accumulation */
+int b200zk_g1_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
+                                   void* stream, void* d_partial128);
+int b200zk_g2_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
+                                   void* stream, void* d_partial256);
 int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags,
                                    void* stream, uint8_t out[64]);
 int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags,

@@ -73,6 +73,8 @@ unsafe extern "C" {
     pub fn b200zk_g2_msm_partial_device(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial256: *mut c_void) -> c_int;
     pub fn b200zk_g1_msm_partial_resident_device(ctx: *mut b200zk_ctx, handle: u64, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial128: *mut c_void) -> c_int;
     pub fn b200zk_g2_msm_partial_resident_device(ctx: *mut b200zk_ctx, handle: u64, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial256: *mut c_void) -> c_int;
+    pub fn b200zk_g1_msm_partial_resident(ctx: *mut b200zk_ctx, handle: u64, scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial128: *mut c_void) -> c_int;
+    pub fn b200zk_g2_msm_partial_resident(ctx: *mut b200zk_ctx, handle: u64, scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial256: *mut c_void) -> c_int;
     pub fn b200zk_g1_fold_partials_device(ctx: *mut b200zk_ctx, d_partials: *const c_void, count: usize, flags: u32, stream: *mut c_void, out: *mut u8) -> c_int;
     pub fn b200zk_g2_fold_partials_device(ctx: *mut b200zk_ctx, d_partials: *const c_void, count: usize, flags: u32, stream: *mut c_void, out: *mut u8) -> c_int;
 

@@ -96,7 +96,7 @@ def main():
             ctx.set_msm_window(0)
             ctx.set_profiling(False)
         # precomputed window tables
-        for log_n, windows in ((20, (17, 18, 19, 20)), (24, (20, 21, 22, 23))):
+        for log_n, windows in ((16, (0,)), (20, (0,)), (24, (0,))):
             n = 1 << log_n
             p, s = dev(8 * n), dev(4 * n)
             ctx.g1_chain_device(p, 0, n, k, dd)
