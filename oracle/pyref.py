@@ -319,3 +319,155 @@ def chain_msm_expected(F, gen, seed: int, scalars):
     for i, s in enumerate(scalars):
         acc = (acc + s * (k + i * d)) % R
     return pt_mul(F, acc, gen)
+
+
+# --------------------------------------------------------------------------- optimal ate pairing (slow, textbook)
+# Only used to replay the reference's own BN254 known-answer tests -- the 14 `ecpairing` vectors of
+# /root/reference/test/tests/levm/precompile_tests.rs:17-140 -- against this file's field/curve arithmetic, which
+# is the arithmetic the MSM fixtures are generated with.  Fq12 = Fq[w]/(w^12 - 18 w^6 + 82) (i.e. w^6 = 9 + u),
+# G2 points are untwisted into Fq12, the Miller loop uses affine line functions, the final exponentiation is a
+# plain power.  ~1-2 s per pairing in CPython: fine for a handful of KATs.
+ATE_LOOP_COUNT = 29793968203157093288
+LOG_ATE_LOOP_COUNT = 63
+_FQ12_MOD = [82, 0, 0, 0, 0, 0, -18, 0, 0, 0, 0, 0]  # w^12 = 18 w^6 - 82
+
+
+def f12(coeffs):
+    c = [int(x) % P for x in coeffs]
+    return c + [0] * (12 - len(c))
+
+
+F12_ONE = f12([1])
+F12_ZERO = f12([0])
+
+
+def f12_add(a, b): return [(x + y) % P for x, y in zip(a, b)]
+def f12_sub(a, b): return [(x - y) % P for x, y in zip(a, b)]
+def f12_neg(a): return [(-x) % P for x in a]
+def f12_scalar(a, k): return [x * k % P for x in a]
+
+
+def f12_mul(a, b):
+    t = [0] * 23
+    for i, x in enumerate(a):
+        if x:
+            for j, y in enumerate(b):
+                t[i + j] += x * y
+    for k in range(22, 11, -1):  # w^k = w^(k-12) * (18 w^6 - 82)
+        v = t[k]
+        if v:
+            t[k - 6] += 18 * v
+            t[k - 12] -= 82 * v
+    return [x % P for x in t[:12]]
+
+
+def _poly_deg(p):
+    d = len(p) - 1
+    while d and p[d] == 0:
+        d -= 1
+    return d
+
+
+def f12_inv(a):
+    """extended Euclid on polynomials over Fq (a != 0)"""
+    lm, hm = [1] + [0] * 12, [0] * 13
+    low, high = a + [0], [x % P for x in _FQ12_MOD] + [1]
+    while _poly_deg(low):
+        # r = high / low (polynomial rounded division)
+        dega, degb = _poly_deg(high), _poly_deg(low)
+        temp, o = high[:], [0] * 13
+        inv_lead = pow(low[degb], -1, P)
+        for i in range(dega - degb, -1, -1):
+            o[i] = (o[i] + temp[degb + i] * inv_lead) % P
+            for c in range(degb + 1):
+                temp[c + i] = (temp[c + i] - o[i] * low[c]) % P
+        r = o[: _poly_deg(o) + 1] + [0] * (13 - _poly_deg(o) - 1)
+        nm, new = hm[:], high[:]
+        for i in range(13):
+            for j in range(13 - i):
+                nm[i + j] = (nm[i + j] - lm[i] * r[j]) % P
+                new[i + j] = (new[i + j] - low[i] * r[j]) % P
+        lm, low, hm, high = nm, new, lm, low
+    inv0 = pow(low[0], -1, P)
+    return [x * inv0 % P for x in lm[:12]]
+
+
+def f12_pow(a, e):
+    r, b = F12_ONE, a
+    while e:
+        if e & 1:
+            r = f12_mul(r, b)
+        b = f12_mul(b, b)
+        e >>= 1
+    return r
+
+
+class _Fq12:
+    zero = F12_ZERO
+    one = F12_ONE
+    add = staticmethod(f12_add)
+    sub = staticmethod(f12_sub)
+    mul = staticmethod(f12_mul)
+    neg = staticmethod(f12_neg)
+    inv = staticmethod(f12_inv)
+    b = f12([3])
+
+
+def _twist(pt):
+    """G2 point over Fq2 (c0 + c1 u) -> the curve y^2 = x^3 + 3 over Fq12 (u = w^6 - 9)."""
+    if pt is None:
+        return None
+    (x0, x1), (y0, y1) = pt
+    nx = f12([x0 - 9 * x1, 0, 0, 0, 0, 0, x1])
+    ny = f12([y0 - 9 * y1, 0, 0, 0, 0, 0, y1])
+    w2, w3 = f12([0, 0, 1]), f12([0, 0, 0, 1])
+    return (f12_mul(nx, w2), f12_mul(ny, w3))
+
+
+def _cast_g1(pt):
+    return None if pt is None else (f12([pt[0]]), f12([pt[1]]))
+
+
+def _linefunc(p1, p2, t):
+    x1, y1 = p1
+    x2, y2 = p2
+    xt, yt = t
+    if x1 != x2:
+        m = f12_mul(f12_sub(y2, y1), f12_inv(f12_sub(x2, x1)))
+        return f12_sub(f12_mul(m, f12_sub(xt, x1)), f12_sub(yt, y1))
+    if y1 == y2:
+        m = f12_mul(f12_scalar(f12_mul(x1, x1), 3), f12_inv(f12_scalar(y1, 2)))
+        return f12_sub(f12_mul(m, f12_sub(xt, x1)), f12_sub(yt, y1))
+    return f12_sub(xt, x1)
+
+
+def miller_loop(q_g2, p_g1):
+    """f_{6x+2,Q}(P) * line corrections, before the final exponentiation; 1 if either point is the identity."""
+    if q_g2 is None or p_g1 is None:
+        return F12_ONE
+    Q, Pt = _twist(q_g2), _cast_g1(p_g1)
+    R, f = Q, F12_ONE
+    for i in range(LOG_ATE_LOOP_COUNT, -1, -1):
+        f = f12_mul(f12_mul(f, f), _linefunc(R, R, Pt))
+        R = pt_add(_Fq12, R, R)
+        if ATE_LOOP_COUNT & (1 << i):
+            f = f12_mul(f, _linefunc(R, Q, Pt))
+            R = pt_add(_Fq12, R, Q)
+    q1 = (f12_pow(Q[0], P), f12_pow(Q[1], P))
+    nq2 = (f12_pow(q1[0], P), f12_neg(f12_pow(q1[1], P)))
+    f = f12_mul(f, _linefunc(R, q1, Pt))
+    R = pt_add(_Fq12, R, q1)
+    f = f12_mul(f, _linefunc(R, nq2, Pt))
+    return f
+
+
+def final_exponentiate(f):
+    return f12_pow(f, (P ** 12 - 1) // R)
+
+
+def pairing_check(pairs) -> bool:
+    """prod e(P_i, Q_i) == 1 -- the ECPAIRING precompile's answer (provider.rs:277-330)."""
+    acc = F12_ONE
+    for g1, g2 in pairs:
+        acc = f12_mul(acc, miller_loop(g2, g1))
+    return final_exponentiate(acc) == F12_ONE

@@ -496,3 +496,29 @@ def test_ntt_2_26_roundtrip_and_direct_evaluation(ctx):
         assert (orc.fr_ntt_eval_output(host_in, log_n, kk) == out[kk]).all(), kk
     ctx.fr_ntt_device(d, log_n, eb.NTT_INVERSE)
     assert torch.equal(d, orig)
+
+
+def test_gpu_msm_on_reference_kat_points_is_bilinear(ctx):
+    """GPU MSMs over the points of the reference's own pairing KATs (tests/golden/pairing_kats.json, BE entry
+    point): the results satisfy e(sum s_i P_i, Q) = prod e(P_i, s_i Q) under the pairing that replays those KATs."""
+    import json, os
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pairing_kats.json")))
+    g1s, g2s = [], []
+    for v in kats["vectors"][:6]:
+        data = bytes.fromhex(v["calldata"])
+        for i in range(0, len(data), 192):
+            g1, g2 = pyref.g1_from_be(data[i:i + 64]), pyref.g2_from_be(data[i + 64:i + 192])
+            if g1 is not None:
+                g1s.append(g1)
+            if g2 is not None:
+                g2s.append(g2)
+    g1s, g2s = g1s[:8], g2s[:4]
+    s = [pyref.rand_fr(91, i) for i in range(8)]
+    sbe = b"".join(pyref.fr_to_be(x) for x in s)
+    a = ctx.g1_msm(b"".join(pyref.g1_to_be(p) for p in g1s), sbe, len(g1s), eb.POINTS_BE | eb.SCALARS_BE)
+    assert a == orc.g1_msm(orc.g1_be_to_native(b"".join(pyref.g1_to_be(p) for p in g1s)), orc.ints_to_array(s))
+    q = pyref.G2_GEN
+    assert pyref.pairing_check([(pyref.g1_from_be(a), q)] + [(pyref.pt_neg(pyref._Fq, p), pyref.g2_mul(x, q)) for p, x in zip(g1s, s)])
+    b = ctx.g2_msm(b"".join(pyref.g2_to_be(p) for p in g2s), sbe[:32 * len(g2s)], len(g2s), eb.POINTS_BE | eb.SCALARS_BE)
+    pneg = pyref.pt_neg(pyref._Fq, pyref.G1_GEN)
+    assert pyref.pairing_check([(pyref.G1_GEN, pyref.g2_from_be(b))] + [(pyref.g1_mul(x, pneg), p) for x, p in zip(s, g2s)])

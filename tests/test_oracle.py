@@ -143,3 +143,52 @@ def test_ntt_eval_output_is_the_definition():
     ai = orc.array_to_ints(orc.fr_from_mont(a))
     w = o.root_of_unity(10)
     assert orc.array_to_ints(orc.fr_from_mont(orc.fr_ntt_eval_output(a, 10, 3).reshape(1, 4)))[0] == sum(v * pow(w, 3 * j, o.R) for j, v in enumerate(ai)) % o.R
+
+
+# ---- the reference's own BN254 KATs (tests/golden/pairing_kats.json, extracted by make_pairing_kats.py) ----
+import json as _json
+
+
+def _pairs(calldata: bytes):
+    return [(o.g1_from_be(calldata[i:i + 64]), o.g2_from_be(calldata[i + 64:i + 192])) for i in range(0, len(calldata), 192)]
+
+
+def test_reference_pairing_kats_replay_on_the_oracle_arithmetic():
+    """All 14 ecpairing vectors of the reference (precompile_tests.rs:17-140): every point decodes (C++ oracle and
+    pyref agree it is on the curve) and the pairing product computed with pyref's field/curve arithmetic gives the
+    expected boolean.  This pins Fq, Fq2, the G1/G2 encodings and both group laws to the reference's own answers."""
+    kats = _json.load(open(os.path.join(GOLD, "pairing_kats.json")))
+    assert len(kats["vectors"]) == 14
+    for v in kats["vectors"]:
+        data = bytes.fromhex(v["calldata"])
+        pairs = _pairs(data)
+        for i, (g1, g2) in enumerate(pairs):
+            assert o.g1_on_curve(g1) and o.g2_on_curve(g2), v["name"]
+            assert orc.g1_native_to_be(orc.g1_be_to_native(data[192 * i:192 * i + 64])) == data[192 * i:192 * i + 64]
+            assert orc.g2_native_to_be(orc.g2_be_to_native(data[192 * i + 64:192 * i + 192])) == data[192 * i + 64:192 * i + 192]
+        assert o.pairing_check(pairs) == bool(v["expected"]), v["name"]
+    oob = bytes.fromhex(kats["coordinate_out_of_bounds_calldata"])
+    with pytest.raises(ValueError, match="status 2"):  # CoordinateExceedsFieldModulus (precompile_tests.rs:143-151)
+        orc.g1_be_to_native(oob[:64])
+
+
+def test_oracle_msm_is_bilinear_under_the_kat_pinned_pairing():
+    """MSM over the reference's KAT points: e(sum s_i P_i, Q) * prod e(-P_i, s_i Q) == 1, with the C++ oracle's
+    Pippenger on the left and pyref scalar multiplications on the right -- ties the MSM oracle to the pairing that
+    the reference's vectors pin (the reference has no MSM vector of its own)."""
+    kats = _json.load(open(os.path.join(GOLD, "pairing_kats.json")))
+    g1s = []
+    for v in kats["vectors"][:5]:
+        g1s += [p for p, _ in _pairs(bytes.fromhex(v["calldata"])) if p is not None]
+    g1s = g1s[:8]
+    scalars = [o.rand_fr(77, i) for i in range(len(g1s))]
+    pts_native = orc.g1_be_to_native(b"".join(o.g1_to_be(p) for p in g1s))
+    a = o.g1_from_be(orc.g1_msm(pts_native, orc.ints_to_array(scalars)))
+    q = o.G2_GEN
+    check = [(a, q)] + [(o.pt_neg(o._Fq, p), o.g2_mul(s, q)) for p, s in zip(g1s, scalars)]
+    assert o.pairing_check(check)
+    # and the G2 side: e(P, sum s_i Q_i) with Q_i = i-th multiples of the KAT G2 generator
+    g2s = [o.g2_mul(i + 2, q) for i in range(4)]
+    b = o.g2_from_be(orc.g2_msm(orc.g2_be_to_native(b"".join(o.g2_to_be(x) for x in g2s)), orc.ints_to_array(scalars[:4])))
+    pneg = o.pt_neg(o._Fq, o.G1_GEN)
+    assert o.pairing_check([(o.G1_GEN, b)] + [(o.g1_mul(s, pneg), x) for s, x in zip(scalars[:4], g2s)])
