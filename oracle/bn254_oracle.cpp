@@ -26,7 +26,9 @@
 // /root/reference/test/tests/levm/precompile_tests.rs:17-24, ALT_BN128_PRIME
 // (/root/reference/crates/vm/levm/src/precompiles.rs:746-751); and the byte conventions of
 // /root/reference/crates/common/crypto/provider.rs:201-330 (32-byte big-endian canonical
-// coordinates, (0,0) = identity, G2 = x_im|x_re|y_im|y_re).  Status codes follow the in-tree
+// coordinates, (0,0) = identity, G2 = x_im|x_re|y_im|y_re); and, through pyref's pairing, the 14 ecpairing
+// KATs of /root/reference/test/tests/levm/precompile_tests.rs:17-140 (every point decodes here; this file's
+// G1/G2 Pippenger results satisfy bilinearity under the pairing that replays those KATs).  Status codes follow the in-tree
 // C-ABI precedent /root/reference/crates/guest-program/src/crypto/zisk.rs:144-172
 // (0 ok, 1 ok-infinity, 2 not in field, 3 not on curve).
 #include <cstdint>

@@ -14,7 +14,11 @@ golden vector.  What *is* pinned by the reference:
     (crates/common/crypto/provider.rs:201-330, crates/vm/levm/src/precompiles.rs:775-799);
   * field modulus ALT_BN128_PRIME (crates/vm/levm/src/precompiles.rs:746-751);
   * on-curve KAT points of test/tests/levm/precompile_tests.rs:17-24 and the
-    ecmul KAT 7*(1,2) of test/tests/l2/integration_tests.rs:572.
+    ecmul KAT 7*(1,2) of test/tests/l2/integration_tests.rs:572;
+  * all 14 `ecpairing` known-answer vectors of test/tests/levm/precompile_tests.rs:17-140
+    (tests/golden/pairing_kats.json): the optimal-ate pairing at the end of this file, built on the same
+    Fq/Fq2/G1/G2 code, reproduces every expected boolean (tests/test_oracle.py), and MSM results are tied to
+    that pairing by bilinearity.
 The MSM/NTT *semantics* restated here are those of the un-vendored third-party
 crates pinned in the reference's Cargo.lock: ark-ec 0.5.0
 `VariableBaseMSM::msm` (result = sum s_i*P_i, normalised to affine) and
