@@ -326,6 +326,19 @@ def run_gpu(args):
                             "binding_roofline": {"bound": "fmaheavy pipe: ~12 modular products per element", "frac": 12 * n / (fwd_ms / 1e3) / 67.7e9},
                             "note": "whole transform (3 passes at 2^24); algorithmic bytes = 64*n; traffic = sum of the three passes' "
                                     "dram bytes from profiles/r1c_prof_ntt_r1b_summary.txt"}}
+        # end to end through the host-buffer C-ABI call: pinned host buffer in, transformed in place, copies included
+        if not args.no_e2e and world == 1:
+            h_ntt = torch.empty(4 * n, dtype=torch.int64).pin_memory()
+            h_ntt.copy_(ref)
+            ctx.fr_ntt(h_ntt, log_n, 0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ctx.fr_ntt(h_ntt, log_n, 0)
+            wall = (time.perf_counter() - t0) / args.steps
+            ntt["e2e"] = {"value": n / wall, "unit": "elements/s", "ms_per_step": wall * 1e3, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
+                          "api": "b200zk_fr_ntt (pinned host buffer, in place): PCIe-bound, 2 x 512 MiB per transform"}
+            del h_ntt
         del d_ntt, ref
 
     # ---- config #5: Groth16-shaped wrap (7 NTT + quotient + 4 G1 MSM + 1 G2 MSM) through B200Backend.prove, N=1

@@ -165,23 +165,46 @@ __global__ void __launch_bounds__(kHistTile) msm_hist(const void* scalars, size_
   }
 }
 
+// kScatterIlp independent entries per thread per iteration: the slot allocation is an L2 atomic WITH return, i.e. a
+// full round trip per entry; with one entry in flight per thread the kernel was latency bound (ncu: long_scoreboard
+// 22.8 stall cycles per issue, LTS 41 % busy), so each thread keeps several allocations in flight.
+static constexpr int kScatterIlp = 4;
 __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ digits, size_t n, MsmPlan pl, uint32_t* cursor, uint32_t* idx) {
   const size_t total = (size_t)pl.W * n;
-  // whole warps stay in the loop together (total is padded per warp) so the match/shuffle below is convergent
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // whole warps stay in the loop together (the bound is padded per warp) so the match/shuffle below is convergent
   const size_t total_pad = (total + 31) & ~(size_t)31;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total_pad; t += (size_t)gridDim.x * blockDim.x) {
-    uint32_t code = t < total ? __ldg(digits + t) : kNoDigit;
-    bool active = code != kNoDigit;
-    size_t w = t / n;  // a warp may straddle two windows at the seam: key on the global bucket id
-    uint32_t g = (pl.merged ? 0u : (uint32_t)(w * pl.B)) + (code & 0x7fffffffu);
-    uint32_t rank, mask;
-    uint32_t cnt = warp_group(g, active, &rank, &mask);
-    uint32_t base = 0;
-    if (active && rank == 0) base = atomicAdd(&cursor[g], cnt);
-    // broadcast the leader's base to its group: leader = lowest lane of the group
-    base = __shfl_sync(mask, base, __ffs(mask) - 1);
-    // merged: the entry addresses the precomputed multiple 2^(c*w) * P_i directly
-    if (active) idx[base + rank] = (uint32_t)((t - w * n) + (pl.merged ? w * pl.table_stride : 0)) | (code & 0x80000000u);
+  for (size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t0 < total_pad; t0 += stride * kScatterIlp) {
+    uint32_t code[kScatterIlp], g[kScatterIlp], rank[kScatterIlp], mask[kScatterIlp], base[kScatterIlp];
+    size_t w[kScatterIlp];
+    bool live[kScatterIlp], active[kScatterIlp];
+#pragma unroll
+    for (int u = 0; u < kScatterIlp; ++u) {
+      const size_t t = t0 + u * stride;
+      live[u] = t < total_pad;  // warp-uniform: stride is a multiple of 32
+      code[u] = (live[u] && t < total) ? __ldg(digits + t) : kNoDigit;
+      active[u] = code[u] != kNoDigit;
+      w[u] = live[u] ? t / n : 0;  // a warp may straddle two windows at the seam: key on the global bucket id
+      g[u] = (pl.merged ? 0u : (uint32_t)(w[u] * pl.B)) + (code[u] & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int u = 0; u < kScatterIlp; ++u) {
+      base[u] = 0; rank[u] = 0; mask[u] = 0;
+      if (live[u]) {
+        uint32_t cnt = warp_group(g[u], active[u], &rank[u], &mask[u]);
+        if (active[u] && rank[u] == 0) base[u] = atomicAdd(&cursor[g[u]], cnt);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScatterIlp; ++u) {
+      if (live[u]) {
+        // broadcast the leader's base to its group: leader = lowest lane of the group
+        uint32_t bs = __shfl_sync(mask[u], base[u], __ffs(mask[u]) - 1);
+        const size_t t = t0 + u * stride;
+        // merged: the entry addresses the precomputed multiple 2^(c*w) * P_i directly
+        if (active[u]) idx[bs + rank[u]] = (uint32_t)((t - w[u] * n) + (pl.merged ? w[u] * pl.table_stride : 0)) | (code[u] & 0x80000000u);
+      }
+    }
   }
 }
 
