@@ -789,6 +789,8 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
     return B200ZK_OK;
   }
   if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+  // 128-bit loads and the bulk copies of the scalar tiles need 16-byte aligned device buffers
+  if (((uintptr_t)d_points & 15) || ((uintptr_t)d_scalars & 15)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: device buffers must be 16-byte aligned");
   MsmPlan pl = make_plan(n, table_c ? table_c : ctx->msm_window);
   if (table_c) {
     pl.merged = 1; pl.Wr = 1; pl.table_stride = (uint32_t)table_stride;

@@ -31,6 +31,7 @@ struct NttTables {
   const uint4* hi;     // hi[y] = w_N^(y << 12)
   const uint4* ninv;   // n^-1
   const uint4* d16;    // d16[x] = w_{2^16}^x, x < 2^16: inter-pass twiddles of passes with Ns*R <= 2^16 in ONE lookup
+  const uint4* lo_n;   // lo_n[x] = lo[x] * n^-1: the last pass of an inverse transform scales through its twiddles
 };
 static constexpr uint32_t kDirectBits = 16;
 
@@ -52,13 +53,22 @@ B2_D Fr root_of_unity(uint32_t log_n) {
   return w;
 }
 
-// entries: [0, 4095) stage tables, then 2^lb lo, then 2^(k-lb) hi, then n^-1, then 2^16 direct
+// entries: [0, 4095) stage tables, then 2^lb lo, then 2^(k-lb) hi, then n^-1, then 2^16 direct, then 2^lb lo * n^-1
 __global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inverse, void* out, uint32_t n_lo, uint32_t n_hi) {
   uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_stage = (1u << kMaxStage) - 1;
   uint32_t total = n_stage + n_lo + n_hi + 1;
-  if (id >= total + (1u << kDirectBits)) return;
+  if (id >= total + (1u << kDirectBits) + n_lo) return;
   Fr val;
+  if (id >= total + (1u << kDirectBits)) {
+    uint32_t e = id - total - (1u << kDirectBits), N = 1u << log_n;
+    if (inverse) e = (N - e) & (N - 1);
+    Fr n = Fr::zero(); n.v[0] = N;
+    val = fr_pow_u32(root_of_unity(log_n), e);
+    if (inverse) val = Fr::mul(val, Fr::inv(Fr::to_mont(n)));
+    store_fe<Fr>(out, id, val);
+    return;
+  }
   if (id >= total) {
     uint32_t x = id - total, D = 1u << kDirectBits;
     val = fr_pow_u32(root_of_unity(kDirectBits), inverse ? (D - x) & (D - 1) : x);
@@ -89,6 +99,7 @@ struct PassArgs {
   void* out;
   uint32_t log_n, s, t, log_ns;
   uint32_t scale_out;  // multiply outputs by n^-1
+  uint32_t scale_in;   // last pass of an inverse transform: n^-1 rides on the inter-pass twiddles (lo_n), no extra product
   uint32_t coset_in;   // first pass of a forward coset transform: element i enters multiplied by h^i
   uint32_t coset_out;  // last pass of an inverse coset transform: element i leaves multiplied by h^-i * n^-1
   const uint4* c_lo;   // coset powers, low table  (base^x, x < 4096; the inverse one carries n^-1)
@@ -115,15 +126,15 @@ B2_D void sts_fr(uint4* sm, uint32_t i, const Fr& a) {
 }
 
 // v * w_{2^L}^(r*jm): one lookup when L <= 16, else two lookups and a product
-B2_D Fr interpass_twiddle(const Fr& v, uint32_t r, uint32_t jm, uint32_t k, uint32_t L, const NttTables& tb) {
+B2_D Fr interpass_twiddle(const Fr& v, uint32_t r, uint32_t jm, uint32_t k, uint32_t L, const NttTables& tb, bool scaled) {
   const uint32_t x = r * jm;
-  if (!x) return v;
+  if (!x) return scaled ? Fr::mul(v, load_fe_nc<Fr>(tb.ninv, 0)) : v;
   Fr tw;
-  if (L <= kDirectBits) {
+  if (L <= kDirectBits) {  // scaled is only requested for L > 16
     tw = load_fe_nc<Fr>(tb.d16, x << (kDirectBits - L));
   } else {
     uint32_t e = x << (k - L);
-    tw = Fr::mul(load_fe_nc<Fr>(tb.lo, e & ((1u << kLoBits) - 1)), load_fe_nc<Fr>(tb.hi, e >> kLoBits));
+    tw = Fr::mul(load_fe_nc<Fr>(scaled ? tb.lo_n : tb.lo, e & ((1u << kLoBits) - 1)), load_fe_nc<Fr>(tb.hi, e >> kLoBits));
   }
   return Fr::mul(v, tw);
 }
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass(PassArgs a) {
   const uint4* stage_tw = a.tb.stage + 2 * ((size_t)(R >> 1) - 1);
   auto first_touch = [&](Fr v, uint32_t row, uint32_t c) -> Fr {
     if (a.coset_in) v = coset_scale(v, (size_t)(j0 + c) + ((size_t)row << stride_log), k, a.c_lo, a.c_hi);  // h^index
-    if (lns) v = interpass_twiddle(v, row, (j0 + c) & ns_mask, k, lns + s, a.tb);  // w_{2^L}^(row * (j mod Ns))
+    if (lns) v = interpass_twiddle(v, row, (j0 + c) & ns_mask, k, lns + s, a.tb, a.scale_in != 0);  // w_{2^L}^(row * (j mod Ns))
     return v;
   };
   uint32_t q = 0;
@@ -287,9 +298,9 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
   auto it = ctx->twiddles.find(key);
   if (it == ctx->twiddles.end()) {
     TwiddleSet ts;
-    ts.bytes = (size_t)(n_stage + n_lo + n_hi + 1 + (1u << kDirectBits)) * 32;
+    ts.bytes = (size_t)(n_stage + n_lo + n_hi + 1 + (1u << kDirectBits) + n_lo) * 32;
     B2_CUDA(ctx, cudaMalloc(&ts.d, ts.bytes));
-    uint32_t total = n_stage + n_lo + n_hi + 1 + (1u << kDirectBits);
+    uint32_t total = n_stage + n_lo + n_hi + 1 + (1u << kDirectBits) + n_lo;
     B2_LAUNCH(ctx, ntt_build_tables, (total + 127) / 128, 128, 0, st, log_n, inverse ? 1 : 0, ts.d, n_lo, n_hi);
     it = ctx->twiddles.emplace(key, ts).first;
   }
@@ -299,6 +310,7 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
   out->hi = out->lo + 2 * (size_t)n_lo;
   out->ninv = out->hi + 2 * (size_t)n_hi;
   out->d16 = out->ninv + 2;
+  out->lo_n = out->d16 + 2 * ((size_t)1 << kDirectBits);
   return B200ZK_OK;
 }
 
@@ -359,6 +371,7 @@ static int launch_pass(b200zk_ctx* ctx, const PassArgs& a, cudaStream_t st) {
 
 int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st) {
   if (log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: log_n > 28 (two-adicity of Fr)");
+  if ((uintptr_t)d_data & 15) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: the device buffer must be 16-byte aligned");
   const size_t n = (size_t)1 << log_n;
   const bool inverse = flags & B200ZK_NTT_INVERSE, coset = flags & B200ZK_NTT_COSET;
   const bool canonical = flags & (B200ZK_NTT_CANONICAL | B200ZK_NTT_BE), be = flags & B200ZK_NTT_BE;
@@ -414,17 +427,22 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
     int cur = 0;
     for (int p = 0; p < pl.P; ++p) {
       PassArgs a;
+      // the last pass reads and writes the same index set per CTA (j + r * 2^(k-s)), after a barrier: it may run in
+      // place, which lands an odd number of passes back in the caller's buffer without a trailing copy
+      const bool last = p == pl.P - 1, in_place = pl.P == 1 || (last && (pl.P & 1));
       a.in = bufs[cur];
-      a.out = pl.P == 1 ? d_data : bufs[cur ^ 1];
+      a.out = in_place ? bufs[cur] : bufs[cur ^ 1];
       a.log_n = log_n; a.s = pl.s[p]; a.t = pl.t[p]; a.log_ns = log_ns;
-      a.scale_out = (inverse && !coset && p == pl.P - 1) ? 1 : 0;
+      const bool fold = inverse && !coset && last && log_ns > 0 && log_n > kDirectBits;
+      a.scale_in = fold ? 1 : 0;
+      a.scale_out = (inverse && !coset && last && !fold) ? 1 : 0;
       a.coset_in = (coset && !inverse && p == 0) ? 1 : 0;
       a.coset_out = (coset && inverse && p == pl.P - 1) ? 1 : 0;
       a.c_lo = (const uint4*)c_lo; a.c_hi = (const uint4*)c_hi;
       a.tb = tb;
       B2_TRY(launch_pass(ctx, a, st));
       log_ns += pl.s[p];
-      if (pl.P > 1) cur ^= 1;
+      if (!in_place) cur ^= 1;
     }
     if (pl.P > 1 && cur == 1) B2_CUDA(ctx, cudaMemcpyAsync(d_data, ctx->ws_ntt.p, n * 32, cudaMemcpyDeviceToDevice, st));
   }

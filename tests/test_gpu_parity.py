@@ -522,3 +522,16 @@ def test_gpu_msm_on_reference_kat_points_is_bilinear(ctx):
     b = ctx.g2_msm(b"".join(pyref.g2_to_be(p) for p in g2s), sbe[:32 * len(g2s)], len(g2s), eb.POINTS_BE | eb.SCALARS_BE)
     pneg = pyref.pt_neg(pyref._Fq, pyref.G1_GEN)
     assert pyref.pairing_check([(pyref.G1_GEN, pyref.g2_from_be(b))] + [(pyref.g1_mul(x, pneg), p) for x, p in zip(s, g2s)])
+
+
+def test_misaligned_device_buffers_are_rejected(ctx):
+    """16-byte alignment is a precondition of the 128-bit loads / bulk copies: violating it is an error, not UB."""
+    import torch
+    buf = torch.zeros(4 * 64 + 1, dtype=torch.int64, device="cuda")
+    pts = torch.zeros(8 * 64, dtype=torch.int64, device="cuda")
+    with pytest.raises(eb.B200Error) as e:
+        ctx.g1_msm_device(pts, buf[1:], 64)     # 8-byte aligned scalars
+    assert e.value.status == 4
+    with pytest.raises(eb.B200Error) as e:
+        ctx.fr_ntt_device(buf[1:1 + 4 * 64], 6, 0)
+    assert e.value.status == 4
