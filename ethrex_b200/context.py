@@ -110,6 +110,47 @@ class Context:
         self._check(F.lib.b200zk_last_msm_phase_ms(self._h, out), "last_msm_phase_ms")
         return dict(zip(("hist", "scan", "scatter", "accumulate", "bucket_reduce", "horner"), (float(x) for x in out)))
 
+    # ------------------------------------------------------------------ batched precompile arithmetic
+    # Twins of Crypto::{bn254_g1_add, bn254_g1_mul, bn254_pairing_check}
+    # (/root/reference/crates/common/crypto/provider.rs:201-330); per-item status as in include/b200zk.h.
+    def bn254_g1_add_batch(self, a: bytes, b: bytes):
+        """a, b: count*64 bytes each -> (count*64 result bytes, [status])"""
+        if len(a) != len(b) or len(a) % 64:
+            raise B200Error.serialization("G1 point must be 64 bytes")
+        count = len(a) // 64
+        out, st = C.create_string_buffer(max(1, 64 * count)), C.create_string_buffer(max(1, count))
+        pa, k1 = _host_ptr(a)
+        pb, k2 = _host_ptr(b)
+        self._check(F.lib.b200zk_bn254_g1_add_batch(self._h, pa, pb, count, out, st), "bn254_g1_add_batch")
+        return out.raw[:64 * count], list(st.raw[:count])
+
+    def bn254_g1_mul_batch(self, points: bytes, scalars: bytes):
+        if len(points) % 64 or len(scalars) != len(points) // 2:
+            raise B200Error.serialization("invalid input length")
+        count = len(points) // 64
+        out, st = C.create_string_buffer(max(1, 64 * count)), C.create_string_buffer(max(1, count))
+        pp, k1 = _host_ptr(points)
+        ps, k2 = _host_ptr(scalars)
+        self._check(F.lib.b200zk_bn254_g1_mul_batch(self._h, pp, ps, count, out, st), "bn254_g1_mul_batch")
+        return out.raw[:64 * count], list(st.raw[:count])
+
+    def bn254_pairing_check_batch(self, checks):
+        """checks: list of calldata byte strings (k*192 bytes each, the ecpairing precompile's input) ->
+        ([result 0/1], [status])"""
+        offs, blob = [0], bytearray()
+        for cd in checks:
+            if len(cd) % 192:
+                raise B200Error.serialization("ecpairing input must be a multiple of 192 bytes")
+            blob += cd
+            offs.append(len(blob) // 192)
+        count = len(checks)
+        offsets = np.asarray(offs, dtype=np.uint32)
+        res, st = C.create_string_buffer(max(1, count)), C.create_string_buffer(max(1, count))
+        pairs = np.frombuffer(bytes(blob) or b"\0", dtype=np.uint8)
+        self._check(F.lib.b200zk_bn254_pairing_check_batch(self._h, pairs.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p),
+                                                          count, res, st), "bn254_pairing_check_batch")
+        return list(res.raw[:count]), list(st.raw[:count])
+
     # ------------------------------------------------------------------ host-buffer entry points
     def g1_msm(self, points, scalars, n: int, flags: int = 0) -> bytes:
         return self._msm_host(F.lib.b200zk_g1_msm, 64, points, scalars, n, flags)

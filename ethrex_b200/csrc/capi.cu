@@ -375,4 +375,18 @@ int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, cons
 int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[64]) { return fold_partials<false>(ctx, d_partials, count, flags, stream, out); }
 int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[128]) { return fold_partials<true>(ctx, d_partials, count, flags, stream, out); }
 
+int b200zk_bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, uint8_t* status) {
+  if (!ctx || (count && (!a || !b || !out || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_g1_add_batch: null argument");
+  return bn254_g1_add_batch(ctx, a, b, count, out, status);
+}
+int b200zk_bn254_g1_mul_batch(b200zk_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t count, uint8_t* out, uint8_t* status) {
+  if (!ctx || (count && (!points || !scalars || !out || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_g1_mul_batch: null argument");
+  return bn254_g1_mul_batch(ctx, points, scalars, count, out, status);
+}
+int b200zk_bn254_pairing_check_batch(b200zk_ctx* ctx, const uint8_t* pairs, const uint32_t* pair_offsets, size_t count, uint8_t* result, uint8_t* status) {
+  if (!ctx || (count && (!pair_offsets || !result || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_pairing_check_batch: null argument");
+  if (count && pair_offsets[count] && !pairs) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_pairing_check_batch: null pairs");
+  return bn254_pairing_check_batch(ctx, pairs, pair_offsets, count, result, status);
+}
+
 }  // extern "C"

@@ -168,5 +168,8 @@ int msm_encode_g1(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_
 int msm_encode_g2(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, cudaStream_t st, void* d_out);
 int points_be_to_native(b200zk_ctx* ctx, const void* d_be, void* d_native, size_t n, bool g2, cudaStream_t st);
 int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st);
+int bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, uint8_t* status);
+int bn254_g1_mul_batch(b200zk_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t count, uint8_t* out, uint8_t* status);
+int bn254_pairing_check_batch(b200zk_ctx* ctx, const uint8_t* pairs, const uint32_t* pair_offsets, size_t count, uint8_t* result, uint8_t* status);
 
 }  // namespace b200zk

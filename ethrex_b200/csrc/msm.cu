@@ -35,6 +35,7 @@ struct MsmPlan {
   uint32_t merged;        // 1: bases carry precomputed 2^(c*w) multiples, all windows share ONE bucket set
   uint32_t Wr;            // bucket sets to reduce: W, or 1 when merged
   uint32_t table_stride;  // merged: bases of window w start at w * table_stride
+  uint32_t adaptive;      // 1: warp aggregation of the sort's atomics only when the warp shows skew (see warp_group)
 };
 
 // window for a precomputed table (all windows share the buckets, so c can be larger: fewer windows)
@@ -63,6 +64,9 @@ static MsmPlan make_plan(size_t n, uint32_t forced_c) {
   p.chunk = p.B < (uint32_t)kChunk ? p.B : (uint32_t)kChunk;
   p.T = p.B / p.chunk;
   p.merged = 0; p.Wr = p.W; p.table_stride = 0;
+  static int adaptive = -1;
+  if (adaptive < 0) { const char* e = getenv("B200ZK_SORT_MATCH"); adaptive = (e && *e == '1') ? 0 : 1; }  // =1: always MATCH (experiment knob)
+  p.adaptive = (uint32_t)adaptive;
   return p;
 }
 
@@ -116,7 +120,23 @@ static constexpr uint32_t kNoDigit = 0xffffffffu;
 
 // One atomic per distinct key per warp: hot buckets (top window, scalars 0/1/small) would otherwise serialise
 // 32 atomics on one L2 address.  Returns the warp-wide count of `key` and this lane's rank within its group.
-B2_D uint32_t warp_group(uint32_t key, bool active, uint32_t* rank, uint32_t* group_mask) {
+// MATCH costs about as many address-divergence-unit cycles as the divergent atomic it saves (ncu r1f: pipe_adu 89 %
+// busy in msm_hist, 73-92 % in msm_scatter), so it only runs when the warp shows skew: `adaptive` first counts the
+// lanes that carry the first active lane's key (one SHFL + one VOTE); fewer than kSkewLanes of them and every lane
+// simply is its own group.  Uniform digits (the prover's case) take the cheap path, a hot bucket the exact one.
+static constexpr uint32_t kSkewLanes = 3;
+B2_D uint32_t warp_group(uint32_t key, bool active, uint32_t* rank, uint32_t* group_mask, bool adaptive) {
+  if (adaptive) {
+    const uint32_t full = __activemask();
+    const uint32_t act = __ballot_sync(full, active);
+    const uint32_t k0 = __shfl_sync(full, key, act ? __ffs(act) - 1 : 0);
+    const uint32_t m0 = __ballot_sync(full, active && key == k0);
+    if (__popc(m0) < kSkewLanes) {
+      *rank = 0;
+      *group_mask = 1u << (threadIdx.x & 31);
+      return 1;
+    }
+  }
   uint32_t mask = __match_any_sync(__activemask(), active ? key : kNoDigit);
   uint32_t lane = threadIdx.x & 31;
   *rank = __popc(mask & ((1u << lane) - 1u));
@@ -158,7 +178,7 @@ __global__ void __launch_bounds__(kHistTile) msm_hist(const void* scalars, size_
       uint32_t code = mag ? ((mag - 1) | neg) : kNoDigit;
       if (live) digits[(size_t)w * n + i] = code;
       uint32_t rank, gm;
-      uint32_t cnt = warp_group(mag - 1, live && mag != 0, &rank, &gm);
+      uint32_t cnt = warp_group(mag - 1, live && mag != 0, &rank, &gm, pl.adaptive != 0);
       if (live && mag && rank == 0) atomicAdd(&hist[(pl.merged ? 0 : (size_t)w * pl.B) + (mag - 1)], cnt);
     }
     __syncthreads();  // everyone is done with tile[buf] before it is refilled two iterations later
@@ -191,7 +211,7 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
     for (int u = 0; u < kScatterIlp; ++u) {
       base[u] = 0; rank[u] = 0; mask[u] = 0;
       if (live[u]) {
-        uint32_t cnt = warp_group(g[u], active[u], &rank[u], &mask[u]);
+        uint32_t cnt = warp_group(g[u], active[u], &rank[u], &mask[u], pl.adaptive != 0);
         if (active[u] && rank[u] == 0) base[u] = atomicAdd(&cursor[g[u]], cnt);
       }
     }

@@ -198,6 +198,29 @@ int b200zk_set_msm_pair_rounds(b200zk_ctx* ctx, int rounds);
 int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]);
 int b200zk_set_profiling(b200zk_ctx* ctx, int enabled);
 
+/* ---- batched EIP-196 / EIP-197 precompile arithmetic ------------------------------
+ * The three BN254 calls of the reference's `Crypto` trait, `count` independent items per call, HOST buffers:
+ *   bn254_g1_add         crates/common/crypto/provider.rs:201-234   (levm ecadd,     crates/vm/levm/src/precompiles.rs:692-716)
+ *   bn254_g1_mul         crates/common/crypto/provider.rs:239-272   (levm ecmul,     precompiles.rs:719-745)
+ *   bn254_pairing_check  crates/common/crypto/provider.rs:277-330   (levm ecpairing, precompiles.rs:821-860)
+ * Encodings: G1 = 64 B big-endian x|y, (0,0) = identity; G2 = 128 B x_im|x_re|y_im|y_re; scalars 32 B big-endian
+ * (any 256-bit value: the group has prime order).  The function's return value reports infrastructure errors only;
+ * input errors are PER ITEM in status[i], with the ZisK-style table (crates/guest-program/src/crypto/zisk.rs:144-172):
+ *   0 ok, 1 ok and the result is the identity, 2 a coordinate >= p (levm: CoordinateExceedsFieldModulus,
+ *   checked for every point of the item before any curve check), 3 a point is not on the curve or (G2) not in the
+ *   order-r subgroup.  Outputs of failed items are zero.
+ * The reference's own vectors for this surface (14 ecpairing cases + the out-of-range case,
+ * test/tests/levm/precompile_tests.rs:17-151; 7*(1,2) of test/tests/l2/integration_tests.rs:572) run through these
+ * entry points in tests/test_gpu_parity.py. */
+int b200zk_bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a /* count*64 */, const uint8_t* b /* count*64 */, size_t count,
+                              uint8_t* out /* count*64 */, uint8_t* status /* count */);
+int b200zk_bn254_g1_mul_batch(b200zk_ctx* ctx, const uint8_t* points /* count*64 */, const uint8_t* scalars /* count*32 */, size_t count,
+                              uint8_t* out /* count*64 */, uint8_t* status /* count */);
+/* check i covers pairs [pair_offsets[i], pair_offsets[i+1]) of `pairs` (192 B each: G1 | G2); result[i] = 1 when
+ * the product of its pairings is one (an empty check is 1), 0 otherwise or when status[i] != 0 */
+int b200zk_bn254_pairing_check_batch(b200zk_ctx* ctx, const uint8_t* pairs, const uint32_t* pair_offsets /* count+1 */, size_t count,
+                                     uint8_t* result /* count */, uint8_t* status /* count */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,8 @@ Mirrors the shape of the reference's precompile KAT tests
 (/root/reference/test/tests/levm/precompile_tests.rs:6-151: feed bytes, compare bytes, check the error
 variant) for the operations of SURVEY.md section 8a rows a6-a8.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -535,3 +537,136 @@ def test_misaligned_device_buffers_are_rejected(ctx):
     with pytest.raises(eb.B200Error) as e:
         ctx.fr_ntt_device(buf[1:1 + 4 * 64], 6, 0)
     assert e.value.status == 4
+
+
+# ---- batched precompile arithmetic: the reference's own vectors through the C ABI ---------------------------------
+def _kats():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pairing_kats.json")))
+
+
+@pytest.mark.gpu
+def test_pairing_check_matches_all_reference_kats(ctx):
+    """The 14 ecpairing vectors of /root/reference/test/tests/levm/precompile_tests.rs:17-140, one batch, through
+    b200zk_bn254_pairing_check_batch: expected booleans are the reference's, not the oracle's."""
+    kats = _kats()
+    checks = [bytes.fromhex(v["calldata"]) for v in kats["vectors"]]
+    res, st = ctx.bn254_pairing_check_batch(checks)
+    assert st == [0] * len(checks)
+    assert res == [v["expected"] for v in kats["vectors"]], [v["name"] for v, r in zip(kats["vectors"], res) if r != v["expected"]]
+
+
+@pytest.mark.gpu
+def test_pairing_check_error_cases(ctx):
+    kats = _kats()
+    good = bytes.fromhex(kats["vectors"][0]["calldata"])
+    oob = bytes.fromhex(kats["coordinate_out_of_bounds_calldata"])  # precompile_tests.rs:143-151
+    oob = oob[:192 * (len(oob) // 192)]
+    # a G1 point off the curve, a G2 point off the curve, and a G2 point on the twist but outside the r-subgroup
+    bad_g1 = (1).to_bytes(32, "big") + (3).to_bytes(32, "big") + good[64:192]
+    bad_g2 = good[:64] + good[64:160] + (int.from_bytes(good[160:192], "big") ^ 1).to_bytes(32, "big")
+    outside = good[:64] + pyref.g2_to_be(_twist_point_outside_subgroup())  # on the twist, not in the r-subgroup
+    res, st = ctx.bn254_pairing_check_batch([good, oob, bad_g1, bad_g2, outside, b"", good + bad_g1, oob + bad_g1])
+    assert st == [0, 2, 3, 3, 3, 0, 3, 2]
+    assert res == [1, 0, 0, 0, 0, 1, 0, 0]
+    # identities on either side contribute one
+    zero_g1 = bytes(64) + good[64:192]
+    zero_g2 = good[:64] + bytes(128)
+    res, st = ctx.bn254_pairing_check_batch([zero_g1, zero_g2, zero_g1 + good])
+    assert st == [0, 0, 0] and res == [1, 1, 1]
+
+
+def _fq_sqrt(v):
+    r = pow(v, (pyref.P + 1) // 4, pyref.P)
+    return r if r * r % pyref.P == v % pyref.P else None
+
+
+def _f2_sqrt(a):
+    """square root in Fq2 = Fq[u]/(u^2+1) by the norm method, or None"""
+    P = pyref.P
+    if a[1] == 0:
+        r = _fq_sqrt(a[0])
+        if r is not None:
+            return (r, 0)
+        r = _fq_sqrt(-a[0] % P)
+        return None if r is None else (0, r)
+    s = _fq_sqrt((a[0] * a[0] + a[1] * a[1]) % P)
+    if s is None:
+        return None
+    half = pow(2, -1, P)
+    for t in ((a[0] + s) * half % P, (a[0] - s) * half % P):
+        x0 = _fq_sqrt(t)
+        if x0:
+            r = (x0, a[1] * pow(2 * x0, -1, P) % P)
+            if pyref.f2_mul(r, r) == (a[0] % P, a[1] % P):
+                return r
+    return None
+
+
+def _twist_point_outside_subgroup():
+    for x in range(1, 400):  # bounded: about half of the x values give a twist point, nearly all of them outside
+        rhs = pyref.f2_add(pyref.f2_mul(pyref.f2_mul((x, 1), (x, 1)), (x, 1)), pyref.B_G2)
+        y = _f2_sqrt(rhs)
+        pt = ((x, 1), y)
+        # pyref.g2_mul reduces its scalar mod r, so r*pt is spelled (r-1)*pt + pt
+        if y is not None and pyref.g2_on_curve(pt) and pyref.g2_add(pyref.g2_mul(pyref.R - 1, pt), pt) is not None:
+            return pt
+    raise AssertionError("no twist point found")
+
+
+@pytest.mark.gpu
+def test_pairing_check_bilinearity_on_fresh_points(ctx):
+    """e(aP, bQ) * e(-(ab)P, Q) == 1 for scalars the KATs never saw; a perturbed product is not one."""
+    import random
+    rng = random.Random(0xB200)
+    checks, want = [], []
+    for k in range(6):
+        a, b = rng.randrange(1, pyref.R), rng.randrange(1, pyref.R)
+        lhs = pyref.g1_to_be(pyref.g1_mul(a, pyref.G1_GEN)) + pyref.g2_to_be(pyref.g2_mul(b, pyref.G2_GEN))
+        good = pyref.g1_to_be(pyref.g1_mul(pyref.R - (a * b) % pyref.R, pyref.G1_GEN)) + pyref.g2_to_be(pyref.G2_GEN)
+        bad = pyref.g1_to_be(pyref.g1_mul(pyref.R - (a * b + 1 + k) % pyref.R, pyref.G1_GEN)) + pyref.g2_to_be(pyref.G2_GEN)
+        checks += [lhs + good, lhs + bad]
+        want += [1, 0]
+    res, st = ctx.bn254_pairing_check_batch(checks)
+    assert st == [0] * len(checks) and res == want
+
+
+@pytest.mark.gpu
+def test_g1_add_mul_batch_vs_reference_kats_and_oracle(ctx):
+    g = pyref.g1_to_be(pyref.G1_GEN)
+    seven_g = bytes.fromhex("17072b2ed3bb8d759a5325f477629386cb6fc6ecb801bd76983a6b86abffe078"
+                            "168ada6cd130dd52017bb54bfa19377aadfe3bf05d18f41b77809f7f60d4af9e")  # integration_tests.rs:572
+    two_g = bytes.fromhex("030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3"
+                          "15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4")
+    neg_g = pyref.g1_to_be((1, pyref.P - 2))
+    off = (1).to_bytes(32, "big") + (3).to_bytes(32, "big")
+    big = pyref.P.to_bytes(32, "big") + (2).to_bytes(32, "big")
+    # ecMul: 7*G (the reference's own KAT), r*G = identity, 0*G, k*identity, (2^256-1)*G, off-curve, out of range
+    pts = g + g + g + bytes(64) + g + off + big
+    ks = [7, pyref.R, 0, 5, (1 << 256) - 1, 3, 3]
+    out, st = ctx.bn254_g1_mul_batch(pts, b"".join(k.to_bytes(32, "big") for k in ks))
+    assert st == [0, 1, 1, 1, 0, 3, 2]
+    assert out[:64] == seven_g and out[64:256] == bytes(192)
+    assert out[256:320] == pyref.g1_to_be(pyref.g1_mul(((1 << 256) - 1) % pyref.R, pyref.G1_GEN))
+    assert out[320:] == bytes(128)
+    # ecAdd: G+G (doubling), G+(-G) (cancellation), G+0, 0+0, 2G+7G vs the oracle, off-curve, out of range
+    a = g + g + g + bytes(64) + two_g + off + g
+    b = g + neg_g + bytes(64) + bytes(64) + seven_g + g + big
+    out, st = ctx.bn254_g1_add_batch(a, b)
+    assert st == [0, 1, 0, 1, 0, 3, 2]
+    assert out[:64] == two_g and out[64:128] == bytes(64) and out[128:192] == g and out[192:256] == bytes(64)
+    rc, nine_g = orc.g1_add_be(two_g, seven_g)
+    assert out[256:320] == nine_g == pyref.g1_to_be(pyref.g1_mul(9, pyref.G1_GEN))
+    # a larger random batch against the C++ oracle
+    n = 300
+    s = orc.rand_fr(0xB2000009, 0, 2 * n)
+    pa = [orc.g1_mul_be(g, orc.limbs_to_int(s[i]).to_bytes(32, "big"))[1] for i in range(n)]
+    kb = [orc.limbs_to_int(s[n + i]).to_bytes(32, "big") for i in range(n)]
+    out, st = ctx.bn254_g1_mul_batch(b"".join(pa), b"".join(kb))
+    assert st == [0] * n
+    for i in range(0, n, 17):
+        assert out[64 * i:64 * i + 64] == orc.g1_mul_be(pa[i], kb[i])[1]
+    out, st = ctx.bn254_g1_add_batch(b"".join(pa), b"".join(reversed(pa)))
+    assert st == [0] * n
+    for i in range(0, n, 13):
+        assert out[64 * i:64 * i + 64] == orc.g1_add_be(pa[i], pa[n - 1 - i])[1]
