@@ -82,12 +82,14 @@ __global__ void __launch_bounds__(256) k_mul32(const uint32_t* in, uint32_t* out
 __global__ void __launch_bounds__(256) k_wide(uint32_t* out, int iters, uint32_t a0) {
   uint64_t acc[8];
   uint32_t a = a0 + threadIdx.x, b = a0 * 3 + blockIdx.x;
-  for (int i = 0; i < 8; ++i) acc[i] = i;
-  for (int it = 0; it < iters; ++it)
+  for (int i = 0; i < 8; ++i) acc[i] = i + 977u * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+    a ^= (uint32_t)acc[0]; b += (uint32_t)(acc[0] >> 32);  // loop-variant operands: nothing to hoist
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+      for (int i = 0; i < 8; ++i) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) & 7]), "r"(b));
+  }
   uint64_t r = 0;
   for (int i = 0; i < 8; ++i) r ^= acc[i];
   if (r == 0x1234567ull) out[0] = (uint32_t)r;
@@ -97,17 +99,19 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_wide_var(uint32_t* out, int iters, uint32_t a0) {
   uint64_t acc[8];
   uint32_t a[8], b[8];
-  for (int i = 0; i < 8; ++i) { acc[i] = i; a[i] = a0 * (i + 3) + threadIdx.x; b[i] = a0 * (i + 11) + blockIdx.x; }
-  for (int it = 0; it < iters; ++it)
+  for (int i = 0; i < 8; ++i) { acc[i] = i + 977u * threadIdx.x; a[i] = a0 * (i + 3) + threadIdx.x; b[i] = a0 * (i + 11) + blockIdx.x; }
+  for (int it = 0; it < iters; ++it) {
+    for (int i = 0; i < 8; ++i) { a[i] ^= (uint32_t)acc[(i + 1) & 7]; b[i] += (uint32_t)(acc[(i + 3) & 7] >> 32); }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (MODE == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i]), "r"(b[0]));        // a distinct, b shared
-        if (MODE == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i]), "r"(b[i]));        // all distinct
-        if (MODE == 2) asm volatile("mad.wide.u32 %0, %1, 0x187cfd47, %0;" : "+l"(acc[i]) : "r"(a[0]));           // shared a, immediate
-        if (MODE == 3) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[(i + u) & 7]), "r"(b[(i * 3 + u) & 7]));  // rotating
+        if (MODE == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) & 7]), "r"(b[0]));        // a = neighbour chain, b shared
+        if (MODE == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) & 7]), "r"(b[i]));        // a = neighbour chain, b[i] distinct
+        if (MODE == 2) asm volatile("mad.wide.u32 %0, %1, 0x187cfd47, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) & 7]));           // immediate multiplier
+        if (MODE == 3) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)(acc[(i + 1) & 7] >> 32)), "r"(b[(i * 3 + u) & 7]));  // a = high word of the neighbour
       }
+  }
   uint64_t r = 0;
   for (int i = 0; i < 8; ++i) r ^= acc[i];
   if (r == 0x1234567ull) out[0] = (uint32_t)r;
@@ -177,7 +181,7 @@ int main(int argc, char** argv) {
   double thr = (double)sms * 8 * 256;
   printf("{\"probe\": \"mad.wide.u32 (64-bit accumulate, no flags)\", \"wide_per_clk_sm\": %.1f}\n", thr * iters * 32 / (mw * 1e-3 * ghz * 1e9 * sms));
   printf("{\"probe\": \"mad.lo.cc/madc.hi.cc chain (IMAD.WIDE.X)\", \"wide_per_clk_sm\": %.1f}\n", thr * iters * 32 / (mc * 1e-3 * ghz * 1e9 * sms));
-  const char* names[4] = {"mad.wide: a[i] distinct, b shared", "mad.wide: a[i], b[i] distinct", "mad.wide: shared a, immediate b", "mad.wide: rotating operands"};
+  const char* names[4] = {"mad.wide: a = neighbour chain, b shared", "mad.wide: a = neighbour chain, b[i] distinct", "mad.wide: a = neighbour chain, immediate b", "mad.wide: a = neighbour high word, b rotating"};
   float v0 = time_kernel(k_wide_var<0>, dim3(sms * 8), dim3(256), out, iters, 3u);
   float v1 = time_kernel(k_wide_var<1>, dim3(sms * 8), dim3(256), out, iters, 3u);
   float v2 = time_kernel(k_wide_var<2>, dim3(sms * 8), dim3(256), out, iters, 3u);

@@ -12,16 +12,21 @@ __global__ void __launch_bounds__(256) probe(uint64_t* out, int iters, uint32_t 
   uint32_t a = a0 + threadIdx.x, b = a0 * 3 + blockIdx.x;
   double da = d0 + threadIdx.x, db = d0 * 0.5;
 #pragma unroll
-  for (int i = 0; i < NI; ++i) acc[i] = i;
+  for (int i = 0; i < NI; ++i) acc[i] = i + 977u * threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < ND; ++i) dac[i] = i;
+  for (int i = 0; i < ND; ++i) dac[i] = i + 0.37 * threadIdx.x;
   for (int it = 0; it < iters; ++it) {
+    // the operands must change every iteration: with loop-invariant a, b ptxas hoists the product out of the loop
+    // and the "multiply-add" degenerates into a 64-bit add (the first version of this probe measured exactly that)
+    if (NI) { a ^= (uint32_t)acc[0]; b += (uint32_t)(acc[0] >> 32); }
+    if (ND) { da += dac[0] * 1e-300; }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
 #pragma unroll
       for (int i = 0; i < (NI > ND ? NI : ND); ++i) {
-        if (i < NI) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
-        if (i < ND) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(dac[i]) : "d"(da), "d"(db));
+        // the multiplicand is the neighbour chain's running value: no two products are alike, nothing can be CSE'd
+        if (i < NI) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) % (NI > 0 ? NI : 1)]), "r"(b));
+        if (i < ND) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(dac[i]) : "d"(dac[(i + 1) % (ND > 0 ? ND : 1)]), "d"(db));
       }
     }
   }
