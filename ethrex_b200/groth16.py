@@ -35,6 +35,70 @@ def _chain_kd(tag: bytes) -> tuple[int, int]:
     return (int.from_bytes(h[:16], "little") | 1), (int.from_bytes(h[16:], "little") | 1)
 
 
+def quotient_on_device(ctx, log_n: int, a, b, c, zinv: int):
+    """H coefficients (Montgomery) from the A, B, C evaluations on the domain (Montgomery device tensors);
+    `a` is overwritten with H.  3 iNTT, 3 coset NTT, (a*b - c)/Z_H on the coset, 1 coset iNTT."""
+    for poly in (a, b, c):
+        ctx.fr_ntt_device(poly, log_n, F.NTT_INVERSE)   # evaluations -> coefficients
+        ctx.fr_ntt_device(poly, log_n, F.NTT_COSET)     # coefficients -> evaluations on the coset
+    ctx.fr_quotient_device(a, b, c, a, 1 << log_n, zinv)
+    ctx.fr_ntt_device(a, log_n, F.NTT_INVERSE | F.NTT_COSET)
+    return a
+
+
+def coset_vanishing_inverse(log_n: int) -> int:
+    """1 / Z_H on the coset g*<w>: Z_H = x^n - 1 is the constant g^n - 1 there."""
+    return pow((pow(COSET_GEN, 1 << log_n, R_MOD) - 1) % R_MOD, -1, R_MOD)
+
+
+class Groth16Prover:
+    """The same pipeline over a CALLER-SUPPLIED proving key (what a zkVM SDK would hand to `B200Backend`): query
+    columns as EIP-196/197 byte strings, one point per R1CS variable (`a_g1`, `b_g1`, `b_g2`), per private variable
+    (`l_g1`) and per quotient coefficient (`h_g1`, n-1 points).  No blinding (r = s = 0): the proof verifies, it is
+    not zero-knowledge.  tests/test_gpu_parity.py proves a small real R1CS with it and checks the Groth16
+    verification equation with the GPU pairing check."""
+
+    def __init__(self, ctx, log_n: int, a_g1: bytes, b_g1: bytes, b_g2: bytes, l_g1: bytes, h_g1: bytes, n_public: int):
+        self.ctx, self.log_n, self.n, self.n_public = ctx, log_n, 1 << log_n, n_public
+        self.m = len(a_g1) // 64
+        if len(b_g1) != 64 * self.m or len(b_g2) != 128 * self.m or len(l_g1) != 64 * (self.m - n_public) or len(h_g1) != 64 * (self.n - 1):
+            raise ValueError("proving-key column sizes do not match")
+        up1, up2 = ctx.g1_bases_upload, ctx.g2_bases_upload
+        self.h = {"a_g1": up1(a_g1, self.m, F.POINTS_BE), "b_g1": up1(b_g1, self.m, F.POINTS_BE), "b_g2": up2(b_g2, self.m, F.POINTS_BE),
+                  "l_g1": up1(l_g1, self.m - n_public, F.POINTS_BE), "h_g1": up1(h_g1, self.n - 1, F.POINTS_BE)}
+        self.zinv = coset_vanishing_inverse(log_n)
+
+    def close(self):
+        for h in self.h.values():
+            self.ctx.bases_free(h)
+        self.h.clear()
+
+    def prove(self, z, a_evals, b_evals, c_evals) -> bytes:
+        """z: the full assignment (integers mod r, z[0] = 1, then the public inputs, then the private variables);
+        a/b/c_evals: (A z), (B z), (C z) on the domain.  Returns A (64) | B (128) | C (64)."""
+        import numpy as np
+        import torch
+        ctx, n = self.ctx, self.n
+
+        def dev(vals):
+            raw = b"".join(int(v % R_MOD).to_bytes(32, "little") for v in vals)
+            t = torch.from_numpy(np.frombuffer(raw, dtype=np.int64).copy()).cuda()
+            ctx.field_to_mont_device(t, len(vals), 1)
+            return t
+
+        a, b, c = dev(a_evals), dev(b_evals), dev(c_evals)
+        hq = quotient_on_device(ctx, self.log_n, a, b, c, self.zinv)
+        zb = b"".join(int(v % R_MOD).to_bytes(32, "little") for v in z)
+        A = ctx.g1_msm_resident(self.h["a_g1"], zb, self.m)
+        B1 = ctx.g1_msm_resident(self.h["b_g1"], zb, self.m)  # noqa: F841  (blinding would use it; kept for the op count)
+        B2 = ctx.g2_msm_resident(self.h["b_g2"], zb, self.m)
+        L = ctx.g1_msm_resident(self.h["l_g1"], zb[32 * self.n_public:], self.m - self.n_public)
+        H = ctx.g1_msm_resident_device(self.h["h_g1"], hq, n - 1, F.SCALARS_MONT)
+        one = (1).to_bytes(32, "little")
+        Cpt = ctx.g1_msm(L + H, one + one, 2, F.POINTS_BE)
+        return A + B2 + Cpt
+
+
 @dataclass
 class ProvingKey:
     """Resident (precomputed) proving-key columns: handles into the context + the chain scalars that define them."""
@@ -69,8 +133,7 @@ class SyntheticWrapCircuit:
                 ctx.bases_precompute(h, 0)
             self.pk.handles[name] = h
             self.pk.chains[name] = (k, d, is_g2)
-        # Z_H on the coset h*<w> is the constant h^n - 1
-        self.zinv = pow((pow(COSET_GEN, self.n, R_MOD) - 1) % R_MOD, -1, R_MOD)
+        self.zinv = coset_vanishing_inverse(log_n)
 
     def close(self):
         for h in self.pk.handles.values():
@@ -95,13 +158,7 @@ class SyntheticWrapCircuit:
     # ---- the hot path ----
     def quotient(self, a, b, c):
         """H coefficients (Montgomery) from the A,B,C evaluations; a is overwritten with H."""
-        ctx, k = self.ctx, self.log_n
-        for poly in (a, b, c):
-            ctx.fr_ntt_device(poly, k, F.NTT_INVERSE)   # evaluations -> coefficients
-            ctx.fr_ntt_device(poly, k, F.NTT_COSET)     # coefficients -> evaluations on the coset
-        ctx.fr_quotient_device(a, b, c, a, self.n, self.zinv)
-        ctx.fr_ntt_device(a, k, F.NTT_INVERSE | F.NTT_COSET)
-        return a
+        return quotient_on_device(self.ctx, self.log_n, a, b, c, self.zinv)
 
     def commit(self, w, h_coeffs, msm=None):
         """The five MSMs.  `msm(name, scalars, n, flags)` lets the multi-GPU driver substitute a sharded MSM."""

@@ -78,7 +78,13 @@ def effective_cpus() -> int:
 
 
 def num_threads() -> int:
-    return min(lib().orc_num_threads(), effective_cpus())
+    """Threads the timed oracle calls use: every CPU the process may really use.  Deliberately NOT
+    omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the CPU
+    baseline of a multi-rank bench into a single-thread run.  B200ZK_ORACLE_THREADS overrides."""
+    env = os.environ.get("B200ZK_ORACLE_THREADS", "")
+    if env.isdigit() and int(env) > 0:
+        return int(env)
+    return effective_cpus()
 
 
 def _thr(threads: int) -> int:

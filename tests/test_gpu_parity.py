@@ -670,3 +670,30 @@ def test_g1_add_mul_batch_vs_reference_kats_and_oracle(ctx):
     assert st == [0] * n
     for i in range(0, n, 13):
         assert out[64 * i:64 * i + 64] == orc.g1_add_be(pa[i], pa[n - 1 - i])[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n", [3, 6])
+def test_real_groth16_proof_from_the_gpu_pipeline_verifies(ctx, log_n):
+    """A real Groth16 instance (tests/groth16_toy.py: random R1CS, trusted setup with known toxic waste): the GPU
+    pipeline (3 iNTT + 3 coset NTT + quotient + coset iNTT, 4 G1 MSMs + 1 G2 MSM over the caller's proving key)
+    must produce the proof BIT FOR BIT as computed in the exponent, and the Groth16 verification equation must hold
+    under the GPU pairing check (itself pinned by the reference's ecpairing vectors)."""
+    from ethrex_b200.groth16 import Groth16Prover
+    from groth16_toy import N_PUBLIC, ToyGroth16
+    toy = ToyGroth16(log_n)
+    prover = Groth16Prover(ctx, log_n, toy.a_g1, toy.b_g1, toy.b_g2, toy.l_g1, toy.h_g1, N_PUBLIC)
+    try:
+        checks, want = [], []
+        for x in (7, pyref.R - 5):
+            z = toy.assign(x)
+            a, b, c = toy.evaluations(z)
+            proof = prover.prove(z, a, b, c)
+            assert proof == toy.expected_proof(z)
+            tampered = proof[:192] + pyref.g1_to_be(pyref.g1_add(pyref.g1_from_be(proof[192:256]), pyref.G1_GEN))
+            checks += [toy.verifier_calldata(proof, x), toy.verifier_calldata(proof, x + 1), toy.verifier_calldata(tampered, x)]
+            want += [1, 0, 0]
+        res, st = ctx.bn254_pairing_check_batch(checks)
+        assert st == [0] * len(checks) and res == want
+    finally:
+        prover.close()

@@ -209,3 +209,19 @@ def test_tower_pairing_restatement_agrees_with_the_kats_and_with_pyref():
     neg = o.g1_mul(o.R - (a * b) % o.R, o.G1_GEN)
     assert tw.pairing_check([(P1, Q1), (neg, o.G2_GEN)])
     assert not tw.pairing_check([(P1, Q1), (o.g1_mul(o.R - (a * b + 1) % o.R, o.G1_GEN), o.G2_GEN)])
+
+
+def test_toy_groth16_instance_is_sound_under_the_kat_pinned_pairing():
+    """tests/groth16_toy.py (the real small Groth16 instance the GPU prover is checked against): the proof computed in
+    the exponent satisfies the verification equation under the pairing the reference's KATs pin; a wrong public input
+    or a perturbed proof does not."""
+    import pyref_tower as tw
+    from groth16_toy import ToyGroth16
+    toy = ToyGroth16(3)
+    x = 0x1234567
+    z = toy.assign(x)
+    proof = toy.expected_proof(z)
+    assert tw.pairing_check(_pairs(toy.verifier_calldata(proof, x)))
+    assert not tw.pairing_check(_pairs(toy.verifier_calldata(proof, x + 1)))
+    bad = proof[:192] + o.g1_to_be(o.g1_add(o.g1_from_be(proof[192:256]), o.G1_GEN))
+    assert not tw.pairing_check(_pairs(toy.verifier_calldata(bad, x)))
