@@ -77,6 +77,7 @@ SIGNATURES = {
     "b200zk_set_msm_pair_rounds": (_int, [_ctx, _int]),
     "b200zk_last_msm_phase_ms": (_int, [_ctx, C.POINTER(C.c_float)]),
     "b200zk_set_profiling": (_int, [_ctx, _int]),
+    "b200zk_msm_multi_resident_device": (_int, [_ctx, _vp, _sz, _vp, _sz, _u32, _vp, _vp, _vp]),
     "b200zk_bn254_g1_add_batch": (_int, [_ctx, _vp, _vp, _sz, _vp, _vp]),
     "b200zk_bn254_g1_mul_batch": (_int, [_ctx, _vp, _vp, _sz, _vp, _vp]),
     "b200zk_bn254_pairing_check_batch": (_int, [_ctx, _vp, _vp, _sz, _vp, _vp]),

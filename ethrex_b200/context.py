@@ -211,6 +211,17 @@ class Context:
     def bases_free(self, handle: int):
         self._check(F.lib.b200zk_bases_free(self._h, handle), "b200zk_bases_free")
 
+    def msm_multi_resident_device(self, handles, is_g2, d_scalars, n: int, flags: int = 0):
+        """MSMs of several resident columns against ONE device scalar vector, sharing the scalar sort.
+        handles: list of base handles; is_g2: matching list of booleans -> list of result byte strings (64 / 128 B)."""
+        count = len(handles)
+        hs = (C.c_uint64 * max(1, count))(*handles)
+        out = C.create_string_buffer(max(1, 128 * count))
+        st = (C.c_int * max(1, count))()
+        self._check(F.lib.b200zk_msm_multi_resident_device(self._h, hs, count, _dev_ptr(d_scalars), n, flags, _current_stream_ptr(), out, st),
+                    "b200zk_msm_multi_resident_device")
+        return [out.raw[128 * i:128 * i + (128 if g2 else 64)] for i, g2 in enumerate(is_g2)]
+
     def g1_msm_resident(self, handle: int, scalars, n: int, flags: int = 0) -> bytes:
         sp, keep = _host_ptr(scalars)
         out = C.create_string_buffer(64)

@@ -375,6 +375,44 @@ int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, cons
 int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[64]) { return fold_partials<false>(ctx, d_partials, count, flags, stream, out); }
 int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[128]) { return fold_partials<true>(ctx, d_partials, count, flags, stream, out); }
 
+int b200zk_msm_multi_resident_device(b200zk_ctx* ctx, const uint64_t* handles, size_t count, const void* d_scalars, size_t n, uint32_t flags,
+                                     void* stream, uint8_t* out, int* status) {
+  if (!ctx || (count && (!handles || !out || !status)) || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: null argument");
+  if (!count) return B200ZK_OK;
+  cudaStream_t st = pick_stream(ctx, stream);
+  const BasesEntry* first = nullptr;
+  for (size_t i = 0; i < count; ++i) {
+    auto it = ctx->bases.find(handles[i]);
+    if (it == ctx->bases.end()) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: unknown handle");
+    const BasesEntry& e = it->second;
+    if (n > e.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: n exceeds the resident bases");
+    if (!first) first = &e;
+    // one sort serves every column only if they share the plan: same window tables (or none) over the same point count
+    if (e.table_c != first->table_c || (e.table_c && e.n != first->n))
+      return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: handles must share the precomputed window and the point count");
+  }
+  B2_TRY(ensure(ctx, ctx->ws_result, 256));
+  B2_TRY(ensure(ctx, ctx->ws_out, 256));
+  for (size_t i = 0; i < count; ++i) {
+    const BasesEntry& e = ctx->bases.find(handles[i])->second;
+    const int mode = (n >= 2) ? (i == 0 ? 1 : 2) : 0;  // n < 2: nothing worth sharing, and the tiny plans differ
+    const uint32_t f = flags & ~(uint32_t)B200ZK_POINTS_BE;
+    int rc;
+    if (e.g2) {
+      B2_TRY(msm_run_g2(ctx, e.d, d_scalars, n, f, st, ctx->ws_result.p, e.table_c, e.n, nullptr, mode));
+      B2_TRY(msm_encode_g2(ctx, ctx->ws_result.p, 1, flags, st, ctx->ws_out.p));
+      rc = read_result(ctx, ctx->ws_out.p, 128, st, out + 128 * i);
+    } else {
+      B2_TRY(msm_run_g1(ctx, e.d, d_scalars, n, f, st, ctx->ws_result.p, e.table_c, e.n, nullptr, mode));
+      B2_TRY(msm_encode_g1(ctx, ctx->ws_result.p, 1, flags, st, ctx->ws_out.p));
+      rc = read_result(ctx, ctx->ws_out.p, 64, st, out + 128 * i);
+    }
+    if (rc > B200ZK_OK_INFINITY) return rc;
+    status[i] = rc;
+  }
+  return B200ZK_OK;
+}
+
 int b200zk_bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, uint8_t* status) {
   if (!ctx || (count && (!a || !b || !out || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_g1_add_batch: null argument");
   return bn254_g1_add_batch(ctx, a, b, count, out, status);

@@ -803,7 +803,10 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
 
 template <class F>
 static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial,
-                   uint32_t table_c, size_t table_stride, const void* h_scalars) {
+                   uint32_t table_c, size_t table_stride, const void* h_scalars, int sort_mode) {
+  // sort_mode (b200zk_msm_multi_resident_device): 0 = ordinary call; 1 = one-shot schedule, the digit sort stays in
+  // the workspaces; 2 = the sort of the previous call (same scalars, same plan) is reused: only the point-dependent
+  // half of the MSM runs (run scan, accumulation, bucket reduction)
   if (n == 0) {
     B2_LAUNCH(ctx, write_identity<F>, 1, 32, 0, st, d_partial);
     return B200ZK_OK;
@@ -824,7 +827,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
     // with HOST scalars 4 chunks hide most of the 512 MiB upload (50.5 -> 41.9 ms)
     uint32_t K = ctx->msm_chunks ? ctx->msm_chunks : ((h_scalars && n >= ((size_t)1 << 22)) ? 4u : 1u);
     if (K > 64) K = 64;
-    if ((K > 1 || h_scalars) && !ctx->profiling && ctx->msm_pair_rounds <= 0 && n >= 4096)
+    if (sort_mode == 0 && (K > 1 || h_scalars) && !ctx->profiling && ctx->msm_pair_rounds <= 0 && n >= 4096)
       return msm_run_pipelined<F>(ctx, d_points, d_scalars, h_scalars, n, flags, st, d_partial, pl, K);
   }
   if (h_scalars) {  // unpipelined path takes device scalars: stage them first
@@ -850,6 +853,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   if (ctx->msm_pair_rounds >= 0) rounds = (uint32_t)ctx->msm_pair_rounds;
   if (rounds > 4) rounds = 4;
   if (rounds && M_max >= ((size_t)1 << 31)) rounds = 0;
+  if (sort_mode) rounds = 0;
   const uint32_t kSegLen = pick_slice_len(M_max >> rounds, (size_t)ctx->sm_count * (sizeof(F) > 32 ? 256 : 512));
   const size_t S_max = (M_max >> rounds) / kSegLen + 1 + G;  // upper bound on the number of runs
   const size_t slices = ((M_max >> rounds) + G + kSegLen - 1) / kSegLen;
@@ -874,17 +878,22 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   uint32_t* idx = (uint32_t*)ctx->ws_idx.p;
 
   phase_mark(ctx, 0, st);
-  B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
-  const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
-  uint32_t* digits = (uint32_t*)ctx->ws_digits.p;
-  B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist, digits);
-  phase_mark(ctx, 1, st);
-  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
-  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
-  B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
-  phase_mark(ctx, 2, st);
-  const unsigned wgrid = (unsigned)std::min<size_t>((n * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
-  B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, st, (const uint32_t*)digits, n, pl, cursor, idx);
+  if (sort_mode != 2) {
+    B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
+    const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    uint32_t* digits = (uint32_t*)ctx->ws_digits.p;
+    B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, d_scalars, n, flags, pl, hist, digits);
+    phase_mark(ctx, 1, st);
+    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
+    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
+    phase_mark(ctx, 2, st);
+    const unsigned wgrid = (unsigned)std::min<size_t>((n * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
+    B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, st, (const uint32_t*)digits, n, pl, cursor, idx);
+  } else {
+    phase_mark(ctx, 1, st);
+    phase_mark(ctx, 2, st);
+  }
   phase_mark(ctx, 3, st);
   // batched-affine pair-summing rounds: each halves the entries the XYZZ accumulation has to fold
   const uint32_t* cur_off = offsets;
@@ -969,8 +978,8 @@ static int precompute_host(b200zk_ctx* ctx, const void* d_bases, size_t n, uint3
 int msm_precompute_g1(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fq>(ctx, b, n, c, t, st); }
 int msm_precompute_g2(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fq2>(ctx, b, n, c, t, st); }
 
-int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs) { return msm_run<Fq>(ctx, p, s, n, f, st, out, tc, ts, hs); }
-int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs) { return msm_run<Fq2>(ctx, p, s, n, f, st, out, tc, ts, hs); }
+int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs, int sort_mode) { return msm_run<Fq>(ctx, p, s, n, f, st, out, tc, ts, hs, sort_mode); }
+int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs, int sort_mode) { return msm_run<Fq2>(ctx, p, s, n, f, st, out, tc, ts, hs, sort_mode); }
 int msm_encode_g1(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq>(ctx, p, c, f, st, out); }
 int msm_encode_g2(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq2>(ctx, p, c, f, st, out); }
 

@@ -177,10 +177,13 @@ class SyntheticWrapCircuit:
             return ctx.g1_msm_resident_device(hnd, scalars, count, flags)
 
         run = msm or local
-        out = {"a_g1": run("a_g1", w, n, 0), "b_g1": run("b_g1", w, n, 0)}
-        if "b_g2" in self.pk.handles:
-            out["b_g2"] = run("b_g2", w, n, 0)
-        out["l_g1"] = run("l_g1", w, n, 0)
+        names = [q for q in ("a_g1", "b_g1", "b_g2", "l_g1") if q in self.pk.handles]
+        if msm is None and self.world == 1:
+            # the four witness MSMs share one scalar sort (b200zk_msm_multi_resident_device)
+            res = ctx.msm_multi_resident_device([self.pk.handles[q] for q in names], [self.pk.chains[q][2] for q in names], w, n, 0)
+            out = dict(zip(names, res))
+        else:
+            out = {q: run(q, w, n, 0) for q in names}
         out["h_g1"] = run("h_g1", h_coeffs, n - 1, F.SCALARS_MONT)
         return out
 

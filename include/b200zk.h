@@ -198,6 +198,15 @@ int b200zk_set_msm_pair_rounds(b200zk_ctx* ctx, int rounds);
 int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]);
 int b200zk_set_profiling(b200zk_ctx* ctx, int enabled);
 
+/* Several resident-base MSMs over ONE scalar vector -- Groth16's [A]1, [B]1, [B]2 and [L]1 all multiply the witness
+ * (the prove step behind crates/prover/src/backend/sp1.rs:97-134 / risc0.rs:71-82).  The scalar-dependent half of
+ * the MSM (digit recoding, bucket histogram, scan, scatter: ~15 % of a 2^24 MSM) runs once and is shared; G1 and G2
+ * handles may be mixed.  All handles must have been precomputed with the same window (or none of them) and, when
+ * precomputed, hold the same number of points.  out: `count` slots of 128 bytes (a G1 result uses the first 64);
+ * status[i] = 0, or 1 when result i is the identity.  Device scalars, like b200zk_g1_msm_resident_device. */
+int b200zk_msm_multi_resident_device(b200zk_ctx* ctx, const uint64_t* handles, size_t count, const void* d_scalars, size_t n,
+                                     uint32_t flags, void* stream, uint8_t* out /* count*128 */, int* status /* count */);
+
 /* ---- batched EIP-196 / EIP-197 precompile arithmetic ------------------------------
  * The three BN254 calls of the reference's `Crypto` trait, `count` independent items per call, HOST buffers:
  *   bn254_g1_add         crates/common/crypto/provider.rs:201-234   (levm ecadd,     crates/vm/levm/src/precompiles.rs:692-716)

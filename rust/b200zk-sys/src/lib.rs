@@ -94,6 +94,7 @@ unsafe extern "C" {
     pub fn b200zk_last_msm_phase_ms(ctx: *mut b200zk_ctx, out_ms: *mut f32) -> c_int;
     pub fn b200zk_set_profiling(ctx: *mut b200zk_ctx, enabled: c_int) -> c_int;
 
+    pub fn b200zk_msm_multi_resident_device(ctx: *mut b200zk_ctx, handles: *const u64, count: usize, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, out: *mut u8, status: *mut c_int) -> c_int;
     pub fn b200zk_bn254_g1_add_batch(ctx: *mut b200zk_ctx, a: *const u8, b: *const u8, count: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn b200zk_bn254_g1_mul_batch(ctx: *mut b200zk_ctx, points: *const u8, scalars: *const u8, count: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn b200zk_bn254_pairing_check_batch(ctx: *mut b200zk_ctx, pairs: *const u8, pair_offsets: *const u32, count: usize, result: *mut u8, status: *mut u8) -> c_int;

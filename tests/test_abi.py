@@ -70,3 +70,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "cpu_oracle" not in txt and "import pyref" not in txt and "libb200zk_oracle" not in txt, f
+
+
+def test_c_demo_fails_loudly_without_a_gpu():
+    """The plain-C demo links against the product library and reports `no CUDA device` (status 6) on this box: the
+    product has no CPU fallback to fall into."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "examples", "build", "c_abi_demo")
+    if not os.path.exists(exe):
+        pytest.skip("examples/build/c_abi_demo not built")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "no CUDA device" in r.stderr

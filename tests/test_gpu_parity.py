@@ -697,3 +697,58 @@ def test_real_groth16_proof_from_the_gpu_pipeline_verifies(ctx, log_n):
         assert st == [0] * len(checks) and res == want
     finally:
         prover.close()
+
+
+@pytest.mark.gpu
+def test_c_abi_from_plain_c():
+    """examples/c_abi_demo.c: the boundary used from C with nothing but include/b200zk.h and libb200zk.so in the
+    process (what a cgo / Rust FFI binding does) -- reference KATs, error statuses, NTT round trip."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "build", "c_abi_demo")
+    assert os.path.exists(exe), "build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precompute", [False, True])
+def test_multi_msm_shares_one_sort_and_matches_single_calls(ctx, precompute):
+    """b200zk_msm_multi_resident_device (Groth16's witness MSMs): G1, G1, G2, G1 columns against one scalar vector
+    give exactly the results of four separate resident MSMs, which are checked against the closed form."""
+    import torch
+    n = 1 << 14
+    cols = []
+    for tag, g2 in ((3, False), (5, False), (7, True), (11, False)):
+        k, d = (chain_kd()[0] * tag) % pyref.R, (chain_kd()[1] + tag) % pyref.R
+        pts = torch.empty((16 if g2 else 8) * n, dtype=torch.int64, device="cuda")
+        (ctx.g2_chain_device if g2 else ctx.g1_chain_device)(pts, 0, n, k, d)
+        h = (ctx.g2_bases_from_device if g2 else ctx.g1_bases_from_device)(pts, n)
+        if precompute:
+            ctx.bases_precompute(h, 0)
+        cols.append((h, g2, k, d))
+    try:
+        for m in (n, n - 37, 2, 1):
+            s = scalars_special(m)
+            ds = to_dev(s)
+            multi = ctx.msm_multi_resident_device([c[0] for c in cols], [c[1] for c in cols], ds, m)
+            for (h, g2, k, d), got in zip(cols, multi):
+                single = (ctx.g2_msm_resident_device if g2 else ctx.g1_msm_resident_device)(h, ds, m)
+                assert got == single
+                assert got == (expected_chain_msm_g2 if g2 else expected_chain_msm_g1)(s, k, d)
+        # a zero vector: every column's result is the identity
+        z = to_dev(np.zeros((8, 4), dtype=np.uint64))
+        multi = ctx.msm_multi_resident_device([c[0] for c in cols], [c[1] for c in cols], z, 8)
+        assert multi == [bytes(128 if c[1] else 64) for c in cols]
+        # mixing a precomputed and a plain column is refused
+        if precompute:
+            pts = torch.empty(8 * n, dtype=torch.int64, device="cuda")
+            ctx.g1_chain_device(pts, 0, n, 3, 5)
+            plain = ctx.g1_bases_from_device(pts, n)
+            with pytest.raises(eb.B200Error) as e:
+                ctx.msm_multi_resident_device([cols[0][0], plain], [False, False], to_dev(scalars_special(8)), 8)
+            assert e.value.status == 4
+            ctx.bases_free(plain)
+    finally:
+        for c in cols:
+            ctx.bases_free(c[0])
