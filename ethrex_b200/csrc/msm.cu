@@ -694,7 +694,7 @@ __global__ void msm_encode(const void* __restrict__ partials, size_t count, bool
   for (size_t k = 0; k < count; ++k) { XYZZ<F> p = load_xyzz<F>(partials, k); xyzz_add(acc, p); }
   Affine<F> a = xyzz_to_affine(acc);
   encode_point(out, a, native);
-  *reinterpret_cast<uint32_t*>(out + 4 * FieldBytes<F>::value) = a.is_inf() ? 1u : 0u;
+  *reinterpret_cast<uint32_t*>(out + 2 * FieldBytes<F>::value) = a.is_inf() ? 1u : 0u;  // right behind the point: read_result()
 }
 
 // ---- host orchestration ---------------------------------------------------------------------------------------

@@ -752,3 +752,23 @@ def test_multi_msm_shares_one_sort_and_matches_single_calls(ctx, precompute):
     finally:
         for c in cols:
             ctx.bases_free(c[0])
+
+
+@pytest.mark.gpu
+def test_msm_entry_points_report_the_identity_as_status_1(ctx):
+    """ZisK-style status table (crates/guest-program/src/crypto/zisk.rs:144-172): 1 = ok, result is the point at
+    infinity.  Checked on the raw return codes of the host, device and resident entry points, G1 and G2."""
+    import ctypes as C
+    from ethrex_b200 import _ffi as F
+    g, g2 = pyref.g1_to_be(pyref.G1_GEN), pyref.g2_to_be(pyref.G2_GEN)
+    five, rm5, one = (5).to_bytes(32, "big"), (pyref.R - 5).to_bytes(32, "big"), (1).to_bytes(32, "big")
+    flags = eb.POINTS_BE | eb.SCALARS_BE
+    out = C.create_string_buffer(128)
+    for pts, fn, size in ((g + g, F.lib.b200zk_g1_msm, 64), (g2 + g2, F.lib.b200zk_g2_msm, 128)):
+        assert fn(ctx._h, pts, five + rm5, 2, flags, out) == 1 and out.raw[:size] == bytes(size)
+        assert fn(ctx._h, pts, five + one, 2, flags, out) == 0 and out.raw[:size] != bytes(size)
+        assert fn(ctx._h, pts, five + rm5, 0, flags, out) == 1 and out.raw[:size] == bytes(size)  # empty sum
+    h = ctx.g1_bases_upload(g + g, 2, eb.POINTS_BE)
+    assert F.lib.b200zk_g1_msm_resident(ctx._h, h, five + rm5, 2, eb.SCALARS_BE, out) == 1
+    assert F.lib.b200zk_g1_msm_resident(ctx._h, h, five + one, 2, eb.SCALARS_BE, out) == 0
+    ctx.bases_free(h)
