@@ -214,20 +214,24 @@ def run_gpu(args):
             fn()
         barrier()
         sampler = ClockSampler(local) if rank == 0 else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         l0 = ctx.launch_count
-        e0.record()
-        for _ in range(steps):
+        evs[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            evs[i + 1].record()  # per-step marks inside the one timed region (min / median / max below)
         barrier()
-        ms = e0.elapsed_time(e1) / steps
+        ms = evs[0].elapsed_time(evs[steps]) / steps
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+        step_stats.update({"min": per[0], "median": per[len(per) // 2], "max": per[-1]})
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), ctx.launch_count - l0, (sampler.stop() if sampler else None)
 
+    step_stats = {}
     ms_step, launches, clocks = timed_loop(msm_step, args.steps, args.warmup)
+    msm_step_stats = dict(step_stats)
     value = world * n / (ms_step / 1e3)
 
     # ---- correctness of what was timed: closed form of the chain MSM (rank 0, outside the timed region)
@@ -384,7 +388,7 @@ def run_gpu(args):
     if rank == 0:
         line = {
             "metric": "bn254_g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "step_ms": msm_step_stats, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 Montgomery (254-bit modular integer)", "data": "synthetic",
             "config": {"workload": f"2^{log_n}-point BN254 G1 MSM per GPU (chain bases P_i=(k+i*d)G, uniform Fr scalars), bases+scalars resident in HBM",
                        "points_per_gpu": n, "total_points": world * n, "l2": "inputs (1.6 GB/GPU) larger than L2; no flush needed",
