@@ -212,8 +212,11 @@ def run_gpu(args):
     def timed_loop(fn, steps, warmup):
         for _ in range(warmup):
             fn()
-        barrier()
+        # start the clock sampler BEFORE the barrier: forking nvidia-smi from a process that maps gigabytes of pinned
+        # memory takes ~100 ms, and with it after the barrier every other rank's timed region absorbed that wait at the
+        # first all_gather (measured at N=8: 61.7 ms "per step" max-over-ranks against 39.9 ms on every rank)
         sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         l0 = ctx.launch_count
         evs[0].record()
