@@ -105,6 +105,77 @@ B2_D void shift_mad_odd(uint32_t* e, uint32_t& x0, uint32_t a1, uint32_t a3, uin
       : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
 }
 
+// ---- truncated rows for the squaring: the multiplicand's low limbs are zero, their products are not issued ----
+// x[2..7] += (a2, a4, a6) * b at columns 2.. (the lower even limbs of the multiplicand are zero)
+B2_D void mad_even_z1(uint32_t* x, uint32_t& top, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
+  asm("mad.lo.cc.u32  %0, %7, %10, %0;\n\t"
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+      "addc.u32       %6, %6, 0;"
+      : "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(top)
+      : "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+// x[4..7] += (a4, a6) * b at columns 4.. (the lower even limbs of the multiplicand are zero)
+B2_D void mad_even_z2(uint32_t* x, uint32_t& top, uint32_t a4, uint32_t a6, uint32_t b) {
+  asm("mad.lo.cc.u32  %0, %5, %7, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32       %4, %4, 0;"
+      : "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(top)
+      : "r"(a4), "r"(a6), "r"(b));
+}
+// x[6..7] += (a6) * b at columns 6.. (the lower even limbs of the multiplicand are zero)
+B2_D void mad_even_z3(uint32_t* x, uint32_t& top, uint32_t a6, uint32_t b) {
+  asm("mad.lo.cc.u32  %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32       %2, %2, 0;"
+      : "+r"(x[6]), "+r"(x[7]), "+r"(top)
+      : "r"(a6), "r"(b));
+}
+B2_D void shift_mad_odd_z1(uint32_t* e, uint32_t& x0, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t b) {
+  asm("add.cc.u32     %8, %8, %1;\n\t"
+      "addc.cc.u32    %0, %2, 0;\n\t"
+      "addc.cc.u32    %1, %3, 0;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %4;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %5;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %6;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %7;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, 0;\n\t"
+      "madc.hi.u32    %7, %11, %12, 0;"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(x0)
+      : "r"(a3), "r"(a5), "r"(a7), "r"(b));
+}
+B2_D void shift_mad_odd_z2(uint32_t* e, uint32_t& x0, uint32_t a5, uint32_t a7, uint32_t b) {
+  asm("add.cc.u32     %8, %8, %1;\n\t"
+      "addc.cc.u32    %0, %2, 0;\n\t"
+      "addc.cc.u32    %1, %3, 0;\n\t"
+      "addc.cc.u32    %2, %4, 0;\n\t"
+      "addc.cc.u32    %3, %5, 0;\n\t"
+      "madc.lo.cc.u32 %4, %9, %11, %6;\n\t"
+      "madc.hi.cc.u32 %5, %9, %11, %7;\n\t"
+      "madc.lo.cc.u32 %6, %10, %11, 0;\n\t"
+      "madc.hi.u32    %7, %10, %11, 0;"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(x0)
+      : "r"(a5), "r"(a7), "r"(b));
+}
+B2_D void shift_mad_odd_z3(uint32_t* e, uint32_t& x0, uint32_t a7, uint32_t b) {
+  asm("add.cc.u32     %8, %8, %1;\n\t"
+      "addc.cc.u32    %0, %2, 0;\n\t"
+      "addc.cc.u32    %1, %3, 0;\n\t"
+      "addc.cc.u32    %2, %4, 0;\n\t"
+      "addc.cc.u32    %3, %5, 0;\n\t"
+      "addc.cc.u32    %4, %6, 0;\n\t"
+      "addc.cc.u32    %5, %7, 0;\n\t"
+      "madc.lo.cc.u32 %6, %9, %10, 0;\n\t"
+      "madc.hi.u32    %7, %9, %10, 0;"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(x0)
+      : "r"(a7), "r"(b));
+}
+
 B2_D void mul_even(uint32_t* x, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t b) {
   asm("mul.lo.u32 %0, %8,  %12;\n\t mul.hi.u32 %1, %8,  %12;\n\t"
       "mul.lo.u32 %2, %9,  %12;\n\t mul.hi.u32 %3, %9,  %12;\n\t"
@@ -230,7 +301,72 @@ struct Fe {
           "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
     return reduce_once(r);
   }
-  static B2_D Fe sqr(const Fe& a) { return mul(a, a); }
+  // Montgomery square: the same rounds as mul(a, a) with the symmetric products issued once.  Row i multiplies a_i
+  // by the vector (0, .., 0, a_i, 2*(a >> 32(i+1))): its limbs are a_i, then d_{i+1} with bit 0 cleared (that bit
+  // is a_i's top bit, which belongs to the part not doubled), then d_j -- d = 2a as limbs (a < 2^254, nothing
+  // leaves limb 7).  36 wide multiply-adds instead of 64 on the product side; the reduction side is unchanged.
+  // Every partial sum is below the full square, and one row is < 2^32 * 2^257, so mul's nine-column bound holds.
+  // Limb-exact Python model of this schedule: tools/field_sqr_model.py; the asm itself is executed in simulation by tools/field_asm_sim.py (tests/test_field_asm_model.py).
+  static B2_D Fe sqr(const Fe& a) {
+    uint32_t d1 = __funnelshift_l(a.v[0], a.v[1], 1), d2 = __funnelshift_l(a.v[1], a.v[2], 1), d3 = __funnelshift_l(a.v[2], a.v[3], 1),
+             d4 = __funnelshift_l(a.v[3], a.v[4], 1), d5 = __funnelshift_l(a.v[4], a.v[5], 1), d6 = __funnelshift_l(a.v[5], a.v[6], 1),
+             d7 = __funnelshift_l(a.v[6], a.v[7], 1);
+    uint32_t ev[8], od[8], m;
+    // round 0: (a0, d1', d2, .., d7) * a0
+    detail::mul_even(ev, a.v[0], d2, d4, d6, a.v[0]);
+    detail::mul_even(od, d1 & ~1u, d3, d5, d7, a.v[0]);
+    m = ev[0] * Cfg::INV;
+    detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 1: (0, a1, d2', d3, .., d7) * a1
+    detail::shift_mad_odd(ev, od[0], a.v[1], d3, d5, d7, a.v[1]);
+    detail::mad_even_z1(od, ev[7], d2 & ~1u, d4, d6, a.v[1]);
+    m = od[0] * Cfg::INV;
+    detail::mad_odd(ev, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(od, ev[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 2: (0, 0, a2, d3', d4, .., d7) * a2
+    detail::shift_mad_odd_z1(od, ev[0], d3 & ~1u, d5, d7, a.v[2]);
+    detail::mad_even_z1(ev, od[7], a.v[2], d4, d6, a.v[2]);
+    m = ev[0] * Cfg::INV;
+    detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 3: (0, 0, 0, a3, d4', d5, d6, d7) * a3
+    detail::shift_mad_odd_z1(ev, od[0], a.v[3], d5, d7, a.v[3]);
+    detail::mad_even_z2(od, ev[7], d4 & ~1u, d6, a.v[3]);
+    m = od[0] * Cfg::INV;
+    detail::mad_odd(ev, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(od, ev[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 4: (.., a4, d5', d6, d7) * a4
+    detail::shift_mad_odd_z2(od, ev[0], d5 & ~1u, d7, a.v[4]);
+    detail::mad_even_z2(ev, od[7], a.v[4], d6, a.v[4]);
+    m = ev[0] * Cfg::INV;
+    detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 5: (.., a5, d6', d7) * a5
+    detail::shift_mad_odd_z2(ev, od[0], a.v[5], d7, a.v[5]);
+    detail::mad_even_z3(od, ev[7], d6 & ~1u, a.v[5]);
+    m = od[0] * Cfg::INV;
+    detail::mad_odd(ev, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(od, ev[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 6: (.., a6, d7') * a6
+    detail::shift_mad_odd_z3(od, ev[0], d7 & ~1u, a.v[6]);
+    detail::mad_even_z3(ev, od[7], a.v[6], a.v[6]);
+    m = ev[0] * Cfg::INV;
+    detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    // round 7: (.., a7) * a7 -- no even limb left
+    detail::shift_mad_odd_z3(ev, od[0], a.v[7], a.v[7]);
+    m = od[0] * Cfg::INV;
+    detail::mad_odd(ev, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(od, ev[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+    Fe r;
+    asm("add.cc.u32  %0, %8,  %16;\n\t addc.cc.u32 %1, %9,  %17;\n\t addc.cc.u32 %2, %10, %18;\n\t addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t addc.cc.u32 %5, %13, %21;\n\t addc.cc.u32 %6, %14, %22;\n\t addc.u32    %7, %15, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+          "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+    return reduce_once(r);
+  }
 
   // a*b + c*d (Montgomery), ONE reduction for the two products: 24 wide multiply-adds per round instead of
   // 2 x 16.  Bound: with all inputs < p the running total stays below 2^256 + 2*2^286 + 2^286 < 2^288 (nine

@@ -29,11 +29,11 @@ __global__ void __launch_bounds__(256) field_convert(void* data, size_t n, int t
   }
 }
 
-template <class Fld>
+template <class Fld, bool SQUARE>
 __global__ void __launch_bounds__(256) field_mul_kernel(const void* a, const void* b, void* out, size_t n, uint32_t repeat) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     Fld x = load_fe<Fld>(a, i), y = load_fe<Fld>(b, i);
-    for (uint32_t r = 0; r < repeat; ++r) x = Fld::mul(x, y);
+    for (uint32_t r = 0; r < repeat; ++r) x = SQUARE ? Fld::sqr(x) : Fld::mul(x, y);
     store_fe<Fld>(out, i, x);
   }
 }
@@ -202,8 +202,12 @@ int b200zk_field_mul_device(b200zk_ctx* ctx, const void* a, const void* b, void*
   if (!repeat) repeat = 1;
   // throughput runs want every SM saturated: no grid cap below n/256
   unsigned grid = (unsigned)((n + 255) / 256);
-  if (which == 0) B2_LAUNCH(ctx, field_mul_kernel<Fq>, grid, 256, 0, st, a, b, out, n, repeat);
-  else B2_LAUNCH(ctx, field_mul_kernel<Fr>, grid, 256, 0, st, a, b, out, n, repeat);
+  // which: bit 0 = field (0 Fq, 1 Fr), bit 1 = squaring (out = a^2, repeated: a^(2^repeat); b is not used)
+  if (which == 0) B2_LAUNCH(ctx, (field_mul_kernel<Fq, false>), grid, 256, 0, st, a, b, out, n, repeat);
+  else if (which == 1) B2_LAUNCH(ctx, (field_mul_kernel<Fr, false>), grid, 256, 0, st, a, b, out, n, repeat);
+  else if (which == 2) B2_LAUNCH(ctx, (field_mul_kernel<Fq, true>), grid, 256, 0, st, a, b, out, n, repeat);
+  else if (which == 3) B2_LAUNCH(ctx, (field_mul_kernel<Fr, true>), grid, 256, 0, st, a, b, out, n, repeat);
+  else return fail(ctx, B200ZK_ERR_INVALID_ARG, "field_mul: which must be 0..3");
   return B200ZK_OK;
 }
 int b200zk_fr_quotient_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n, const uint8_t zinv[32], void* stream) {

@@ -165,7 +165,8 @@ int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size
 int b200zk_field_to_mont_device(b200zk_ctx* ctx, void* d_data, size_t n, int which, void* stream);
 int b200zk_field_from_mont_device(b200zk_ctx* ctx, void* d_data, size_t n, int which, void* stream);
 /* out[i] = a[i] * b[i] (Montgomery product), the field core exposed for parity tests and microbenchmarks;
- * `repeat` > 1 chains out = out * b that many times (throughput measurement) */
+ * `repeat` > 1 chains out = out * b that many times (throughput measurement).
+ * which: 0 = Fq, 1 = Fr; +2 = the dedicated squaring instead (out = a^2, chained: a^(2^repeat); d_b is read but unused) */
 int b200zk_field_mul_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, void* d_out, size_t n,
                             int which, uint32_t repeat, void* stream);
 /* out[i] = (a[i]*b[i] - c[i]) * zinv over Fr (Montgomery data; zinv canonical LE): the pointwise step of the

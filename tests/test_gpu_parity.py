@@ -44,6 +44,21 @@ def test_field_mul_matches_oracle(ctx, which, field):
     for _ in range(5):
         exp = orc.field_mul(field, exp, b)
     assert (to_host(do).reshape(n, 4) == exp).all()
+    # the dedicated squaring (36 instead of 64 products) against the oracle's a*a, once and chained; extra edge
+    # values exercise every limb's top bit (the doubled multiplicand) and the all-ones patterns
+    more = [(mod - 1) >> 1, ((1 << 254) - 1) % mod, 0x80000000, (0x80000000 << 32) | 0x80000000, sum(0x80000000 << (32 * k) for k in range(8)) % mod,
+            sum(0xffffffff << (32 * k) for k in range(7)), (mod >> 1) + 1]
+    for i, e in enumerate(more):
+        vals_a[len(edge) + i] = e % mod
+    a = orc.ints_to_array(vals_a)
+    da = to_dev(a)
+    ctx.field_mul_device(da, db, do, n, which + 2)
+    assert (to_host(do).reshape(n, 4) == orc.field_mul(field, a, a)).all()
+    ctx.field_mul_device(da, db, do, n, which + 2, repeat=4)
+    exp = a
+    for _ in range(4):
+        exp = orc.field_mul(field, exp, exp)
+    assert (to_host(do).reshape(n, 4) == exp).all()
 
 
 def test_mont_roundtrip_and_random(ctx):
