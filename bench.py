@@ -269,13 +269,16 @@ def run_gpu(args):
     traffic = 29.340339e9 + 0.198330e9 if (log_n == 24 and not args.no_precompute and not args.window) else None
     MODMUL_PEAK = 67.7e9  # measured 254-bit Montgomery products/s of the chip (profiles/r1_probe_field_mul.md)
     adds = n * 13 if (not args.no_precompute and not args.window and log_n >= 20) else None
+    # multiply instructions of one XYZZ mixed addition, in units of one Montgomery product (136 IMAD-type
+    # instructions): 6 products + one two-product/one-reduction mul2 (200) + 2 dedicated squarings (108 each)
+    PE = (6 * 136 + 200 + 2 * 108) / 136.0
     roofline = {"bound": "hbm", "kernel": "msm_accumulate<Fq>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": acc, "phases_ms": phases,
                 "binding_roofline": {"bound": "fmaheavy pipe (IMAD.WIDE): 254-bit modular products", "peak_products_per_s": MODMUL_PEAK,
-                                     "achieved_products_per_s": (adds * 9.5 / (acc / 1e3)) if adds else None,
-                                     "frac": (adds * 9.5 / (acc / 1e3) / MODMUL_PEAK) if adds else None,
+                                     "achieved_products_per_s": (adds * PE / (acc / 1e3)) if adds else None,
+                                     "frac": (adds * PE / (acc / 1e3) / MODMUL_PEAK) if adds else None,
                                      "ncu_sm__pipe_fmaheavy_cycles_active_pct": 92.3},
-                "note": "integer-compute-bound kernel (n*13 XYZZ mixed additions of 9.5 product-equivalents): the HBM fraction is small by "
+                "note": "integer-compute-bound kernel (n*13 XYZZ mixed additions of 9.06 product-equivalents: 6 products, one mul2, 2 squarings): the HBM fraction is small by "
                         "construction, see DESIGN.md section 4; kernel_ms is measured in the one-shot schedule (phases are not separable "
                         "in the chunk-pipelined one that `value` runs)"}
 
