@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+LIB_PATH = os.environ.get("B200ZK_LIB") or os.path.join(_HERE, "libb200zk.so")  # B200ZK_LIB: A/B builds of the same ABI (experiments)
 
 # status codes (include/b200zk.h; 0..3 = /root/reference/crates/guest-program/src/crypto/zisk.rs:144-172)
 OK, OK_INFINITY, ERR_NOT_IN_FIELD, ERR_NOT_ON_CURVE, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_UNSUPPORTED = range(9)

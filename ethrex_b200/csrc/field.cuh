@@ -449,11 +449,19 @@ struct Fq2 {
   static B2_D Fq2 sub(const Fq2& a, const Fq2& b) { return {Fq::sub(a.c0, b.c0), Fq::sub(a.c1, b.c1)}; }
   static B2_D Fq2 dbl(const Fq2& a) { return {Fq::dbl(a.c0), Fq::dbl(a.c1)}; }
   static B2_D Fq2 neg(const Fq2& a) { return {Fq::neg(a.c0), Fq::neg(a.c1)}; }
+#ifdef B200ZK_FQ2_MUL2
+  // schoolbook with ONE reduction per component: c0 = a0 b0 + (p - a1) b1, c1 = a0 b1 + a1 b0 (2 x 200 multiply
+  // instructions, one negation) -- against Karatsuba's 3 x 136 and five additions/subtractions with their temporaries
+  static B2_D Fq2 mul(const Fq2& a, const Fq2& b) {
+    return {Fq::mul2_add(a.c0, b.c0, Fq::neg(a.c1), b.c1), Fq::mul2_add(a.c0, b.c1, a.c1, b.c0)};
+  }
+#else
   static B2_D Fq2 mul(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 base multiplications
     Fq t0 = Fq::mul(a.c0, b.c0), t1 = Fq::mul(a.c1, b.c1);
     Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
     return {Fq::sub(t0, t1), Fq::sub(Fq::sub(s, t0), t1)};
   }
+#endif
   static B2_D Fq2 sqr(const Fq2& a) {  // (c0+c1)(c0-c1), 2 c0 c1
     Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
     return {Fq::mul(s, d), Fq::dbl(m)};

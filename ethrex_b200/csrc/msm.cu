@@ -28,6 +28,7 @@ namespace b200zk {
 
 static constexpr int kMaxWindows = 64;
 static constexpr int kChunk = 32;  // buckets per running-sum chunk
+static constexpr int kG2MinBlocks = 1;  // register cap of msm_accumulate<Fq2> (see the launch site)
 
 struct MsmPlan {
   uint32_t c, W, B;       // window bits, windows, buckets per window (2^(c-1))
@@ -346,8 +347,8 @@ B2_D uint32_t bucket_of(const uint32_t* __restrict__ offsets, uint32_t G, uint32
 
 // DIRECT: `points` is already the sorted, sign-applied entry array (output of pair_sum); else entries are
 // idx[e] = base index | sign << 31 into the bases / window table.
-template <class F, bool DIRECT>
-__global__ void __launch_bounds__(128) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
+template <class F, bool DIRECT, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) msm_accumulate(const void* __restrict__ points, const uint32_t* __restrict__ idx,
                                                       const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ run_off,
                                                       uint32_t G, uint32_t kSegLen, void* __restrict__ partials, uint32_t* __restrict__ run_bucket) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -917,7 +918,21 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
   B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, cur_off, G, kSegLen, 0u, tsum, seg_off, (uint32_t*)nullptr);
   if (rounds) B2_LAUNCH(ctx, (msm_accumulate<F, true>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
-  else B2_LAUNCH(ctx, (msm_accumulate<F, false>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+  else {
+    // G2: the uncapped build takes 255 registers (2 CTAs = 8 warps per SM); MINB caps it at 168 / 128 for 3 / 4 CTAs.
+    // Experiment knob B200ZK_G2_MINB=1|2|3|4 (Fq2 only; measured in profiles/r1h_g2_occupancy.md)
+    static int g2_minb = 0;
+    if (!g2_minb) { const char* e = getenv("B200ZK_G2_MINB"); g2_minb = (e && *e >= '1' && *e <= '4') ? (*e - '0') : kG2MinBlocks; }
+    const unsigned agrid = (unsigned)((slices + 127) / 128);
+    if constexpr (sizeof(F) > 32) {
+      if (g2_minb == 4) B2_LAUNCH(ctx, (msm_accumulate<F, false, 4>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+      else if (g2_minb == 3) B2_LAUNCH(ctx, (msm_accumulate<F, false, 3>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+      else if (g2_minb == 2) B2_LAUNCH(ctx, (msm_accumulate<F, false, 2>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+      else B2_LAUNCH(ctx, (msm_accumulate<F, false, 1>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+    } else {
+      B2_LAUNCH(ctx, (msm_accumulate<F, false>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
+    }
+  }
   {
     // worst case every point of a window lands in one bucket: ceil(entries / kSegLen) + 1 runs to fold
     size_t worst_entries = ((pl.merged ? n * (size_t)pl.W : n) >> rounds) + 1;
