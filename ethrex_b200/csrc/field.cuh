@@ -409,6 +409,59 @@ struct Fe {
           "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
     return reduce_once(r);
   }
+  // a*b + c*d + e*f + g*h (Montgomery), ONE reduction for the four products: 40 wide multiply-adds per round instead
+  // of 4 x 16.  Bound (both moduli are 0.756 * 2^254): a round adds at most 4 * p * 2^32 + p * 2^32 = 0.945 * 2^288 to a
+  // running total below 2^256, so the nine columns still hold it, and the result is < 4p^2/2^256 + p = 1.76p: one
+  // conditional subtraction.  Checked at the worst case ((p-1)^2 four times) by tools/field_sqr_model.py.
+  // Fq2's a*b - c*d uses it for each of its two components.
+  static B2_D Fe mul4_add(const Fe& a, const Fe& b, const Fe& c, const Fe& d, const Fe& e, const Fe& f, const Fe& g, const Fe& h) {
+    const Fe* const x[4] = {&a, &c, &e, &g};
+    const Fe* const y[4] = {&b, &d, &f, &h};
+    uint32_t ev[8], od[8];
+    uint32_t m;
+    detail::mul_even(ev, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+    detail::mul_even(od, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      detail::mad_odd(od, x[k]->v[1], x[k]->v[3], x[k]->v[5], x[k]->v[7], y[k]->v[0]);
+      detail::mad_even(ev, od[7], x[k]->v[0], x[k]->v[2], x[k]->v[4], x[k]->v[6], y[k]->v[0]);
+    }
+    m = ev[0] * Cfg::INV;
+    detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+    detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+      detail::shift_mad_odd(ev, od[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+      detail::mad_even(od, ev[7], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        detail::mad_odd(ev, x[k]->v[1], x[k]->v[3], x[k]->v[5], x[k]->v[7], y[k]->v[i]);
+        detail::mad_even(od, ev[7], x[k]->v[0], x[k]->v[2], x[k]->v[4], x[k]->v[6], y[k]->v[i]);
+      }
+      m = od[0] * Cfg::INV;
+      detail::mad_odd(ev, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+      detail::mad_even(od, ev[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+      if (i + 1 < 8) {
+        detail::shift_mad_odd(od, ev[0], a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+        detail::mad_even(ev, od[7], a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          detail::mad_odd(od, x[k]->v[1], x[k]->v[3], x[k]->v[5], x[k]->v[7], y[k]->v[i + 1]);
+          detail::mad_even(ev, od[7], x[k]->v[0], x[k]->v[2], x[k]->v[4], x[k]->v[6], y[k]->v[i + 1]);
+        }
+        m = ev[0] * Cfg::INV;
+        detail::mad_odd(od, Cfg::mod(1), Cfg::mod(3), Cfg::mod(5), Cfg::mod(7), m);
+        detail::mad_even(ev, od[7], Cfg::mod(0), Cfg::mod(2), Cfg::mod(4), Cfg::mod(6), m);
+      }
+    }
+    Fe r;
+    asm("add.cc.u32  %0, %8,  %16;\n\t addc.cc.u32 %1, %9,  %17;\n\t addc.cc.u32 %2, %10, %18;\n\t addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t addc.cc.u32 %5, %13, %21;\n\t addc.cc.u32 %6, %14, %22;\n\t addc.u32    %7, %15, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+          "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+    return reduce_once(r);
+  }
   // a*b - c*d
   static B2_D Fe mul2_sub(const Fe& a, const Fe& b, const Fe& c, const Fe& d) { return mul2_add(a, b, neg(c), d); }
 
@@ -449,25 +502,27 @@ struct Fq2 {
   static B2_D Fq2 sub(const Fq2& a, const Fq2& b) { return {Fq::sub(a.c0, b.c0), Fq::sub(a.c1, b.c1)}; }
   static B2_D Fq2 dbl(const Fq2& a) { return {Fq::dbl(a.c0), Fq::dbl(a.c1)}; }
   static B2_D Fq2 neg(const Fq2& a) { return {Fq::neg(a.c0), Fq::neg(a.c1)}; }
-#ifdef B200ZK_FQ2_MUL2
-  // schoolbook with ONE reduction per component: c0 = a0 b0 + (p - a1) b1, c1 = a0 b1 + a1 b0 (2 x 200 multiply
-  // instructions, one negation) -- against Karatsuba's 3 x 136 and five additions/subtractions with their temporaries
+  // Schoolbook with ONE reduction per component: c0 = a0 b0 + (p - a1) b1, c1 = a0 b1 + a1 b0 -- 2 x 200 multiply
+  // instructions and one negation.  Karatsuba (3 x 136 and five additions/subtractions with their temporaries) was
+  // the first version: measured on B200, the G2 MSM accumulation went 35.1 -> 30.4 ms at 2^22 with this form
+  // (profiles/r1h_g2.md); the register pressure of the temporaries cost more than the 8 multiply instructions saved.
   static B2_D Fq2 mul(const Fq2& a, const Fq2& b) {
     return {Fq::mul2_add(a.c0, b.c0, Fq::neg(a.c1), b.c1), Fq::mul2_add(a.c0, b.c1, a.c1, b.c0)};
   }
-#else
-  static B2_D Fq2 mul(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 base multiplications
-    Fq t0 = Fq::mul(a.c0, b.c0), t1 = Fq::mul(a.c1, b.c1);
-    Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
-    return {Fq::sub(t0, t1), Fq::sub(Fq::sub(s, t0), t1)};
-  }
-#endif
   static B2_D Fq2 sqr(const Fq2& a) {  // (c0+c1)(c0-c1), 2 c0 c1
     Fq s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
     return {Fq::mul(s, d), Fq::dbl(m)};
   }
-  // a*b - c*d over Fq2 (no merged form yet: the base-field reductions are already shared inside mul)
-  static B2_D Fq2 mul2_sub(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return sub(mul(a, b), mul(c, d)); }
+  // a*b - c*d over Fq2: each component is a sum of FOUR base-field products under one reduction (Fq::mul4_add):
+  //   re = a0 b0 - a1 b1 - c0 d0 + c1 d1        im = a0 b1 + a1 b0 - c0 d1 - c1 d0
+  static B2_D Fq2 mul2_sub(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) {
+#ifdef B200ZK_FQ2_NO_MUL4
+    return sub(mul(a, b), mul(c, d));
+#else
+    const Fq na1 = Fq::neg(a.c1), nc0 = Fq::neg(c.c0), nc1 = Fq::neg(c.c1);
+    return {Fq::mul4_add(a.c0, b.c0, na1, b.c1, nc0, d.c0, c.c1, d.c1), Fq::mul4_add(a.c0, b.c1, a.c1, b.c0, nc0, d.c1, nc1, d.c0)};
+#endif
+  }
   static B2_D Fq2 inv(const Fq2& a) {
     Fq d = Fq::inv(Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1)));
     return {Fq::mul(a.c0, d), Fq::neg(Fq::mul(a.c1, d))};

@@ -82,3 +82,45 @@ for t in range(3000):
     assert mont(a,b)==a*b*Rinv%P
     assert mont(a,a,sqr_rows(a))==a*a*Rinv%P, hex(a)
 print("model ok: even/odd CIOS product and the 36-product squaring agree with big-int arithmetic")
+
+# ---- mul4_add: a*b + c*d + e*f + g*h with ONE reduction (bound check with worst-case inputs) ----------------
+def mont_sum(pairs):
+    pe=[pl[0],pl[2],pl[4],pl[6]]; po=[pl[1],pl[3],pl[5],pl[7]]
+    L=[(limbs(a),limbs(b)) for a,b in pairs]
+    ev=[0]*8; od=[0]*8
+    first=True
+    A,B=ev,od
+    for i in range(8):
+        for k,(al,bl) in enumerate(L):
+            e_=[al[0],al[2],al[4],al[6]]; o_=[al[1],al[3],al[5],al[7]]
+            if i==0:
+                if k==0:
+                    chain(A,0,[x*bl[0] for x in e_]); chain(B,0,[x*bl[0] for x in o_])
+                else:
+                    mad_odd(B,o_,bl[0]); B[7]=mad_even(A,B[7],e_,bl[0]); assert B[7]<=M32
+            else:
+                if k==0:
+                    B[0]=shift_mad_odd(A,B[0],o_,bl[i])   # A becomes the odd accumulator
+                    A[7]=mad_even(B,A[7],e_,bl[i]); assert A[7]<=M32
+                else:
+                    mad_odd(A,o_,bl[i]); A[7]=mad_even(B,A[7],e_,bl[i]); assert A[7]<=M32
+        if i==0:
+            m=(A[0]*INV)&M32
+            mad_odd(B,po,m); B[7]=mad_even(A,B[7],pe,m); assert B[7]<=M32
+        else:
+            m=(B[0]*INV)&M32
+            mad_odd(A,po,m); A[7]=mad_even(B,A[7],pe,m); assert A[7]<=M32
+            A,B=B,A
+    r=(val(A)>>32)+val(B)
+    assert r<2*P, "more than one subtraction needed"
+    if r>=P: r-=P
+    return r
+for t in range(2000):
+    if t<4: vals=[P-1]*8
+    elif t<8: vals=[P-1 if (t>>k)&1 else random.randrange(P) for k in range(8)]
+    else: vals=[random.randrange(P) for _ in range(8)]
+    pairs=[(vals[0],vals[1]),(vals[2],vals[3]),(vals[4],vals[5]),(vals[6],vals[7])]
+    exp=sum(a*b for a,b in pairs)*Rinv%P
+    assert mont_sum(pairs)==exp
+    assert mont_sum(pairs[:2])==sum(a*b for a,b in pairs[:2])*Rinv%P
+print("model ok: four-product sum with one reduction (no lost carry at the worst case (p-1)^2 x 4, result < 2p)")
