@@ -27,7 +27,7 @@
 namespace b200zk {
 
 static constexpr int kMaxWindows = 64;
-static constexpr int kChunk = 32;  // buckets per running-sum chunk
+static constexpr int kChunk = 16;  // buckets per running-sum chunk (measured 8/16/32/64: profiles/r1h_g2.md)
 static constexpr int kG2MinBlocks = 1;  // register cap of msm_accumulate<Fq2> (see the launch site)
 
 struct MsmPlan {
@@ -62,7 +62,10 @@ static MsmPlan make_plan(size_t n, uint32_t forced_c) {
   p.c = c;
   p.W = (255 + c - 1) / c;
   p.B = 1u << (c - 1);
-  p.chunk = p.B < (uint32_t)kChunk ? p.B : (uint32_t)kChunk;
+  static int chunk_knob = -1;  // experiment knob B200ZK_CHUNK=8|16|32|64: buckets per running-sum chunk
+  if (chunk_knob < 0) { const char* e = getenv("B200ZK_CHUNK"); chunk_knob = e ? atoi(e) : 0; if (chunk_knob & (chunk_knob - 1)) chunk_knob = 0; }
+  const uint32_t want_chunk = chunk_knob > 0 ? (uint32_t)chunk_knob : (uint32_t)kChunk;
+  p.chunk = p.B < want_chunk ? p.B : want_chunk;
   p.T = p.B / p.chunk;
   p.merged = 0; p.Wr = p.W; p.table_stride = 0;
   static int adaptive = -1;
