@@ -127,6 +127,89 @@ impl B200zk {
     }
 }
 
+/// Per-item outcome of the batched precompile calls (include/b200zk.h: 0 ok, 1 ok-identity, 2 coordinate >= p,
+/// 3 not on the curve / not in the subgroup).
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum ItemStatus {
+    Ok,
+    OkIdentity,
+    NotInField,
+    NotOnCurve,
+}
+
+impl ItemStatus {
+    fn from_code(code: u8) -> Self {
+        match code {
+            0 => Self::Ok,
+            1 => Self::OkIdentity,
+            2 => Self::NotInField,
+            _ => Self::NotOnCurve,
+        }
+    }
+}
+
+impl B200zk {
+    /// `count` independent ecAdd items: `a`, `b` = count x 64 bytes.  Returns (count x 64 result bytes, per-item status).
+    pub fn bn254_g1_add_batch(&mut self, a: &[u8], b: &[u8]) -> Result<(Vec<u8>, Vec<ItemStatus>), BackendError> {
+        if a.len() != b.len() || a.len() % 64 != 0 {
+            return Err(BackendError::serialization("bn254_g1_add_batch: inputs must be equal multiples of 64 bytes"));
+        }
+        let count = a.len() / 64;
+        let mut out = vec![0u8; a.len()];
+        let mut st = vec![0u8; count];
+        // SAFETY: all four buffers hold `count` items of the documented sizes and outlive the synchronous call.
+        let status = unsafe { sys::b200zk_bn254_g1_add_batch(self.ctx.as_ptr(), a.as_ptr(), b.as_ptr(), count, out.as_mut_ptr(), st.as_mut_ptr()) };
+        check(self, status)?;
+        Ok((out, st.into_iter().map(ItemStatus::from_code).collect()))
+    }
+
+    /// `count` independent ecMul items: `points` = count x 64 bytes, `scalars` = count x 32 bytes (big-endian).
+    pub fn bn254_g1_mul_batch(&mut self, points: &[u8], scalars: &[u8]) -> Result<(Vec<u8>, Vec<ItemStatus>), BackendError> {
+        if points.len() % 64 != 0 || scalars.len() != points.len() / 2 {
+            return Err(BackendError::serialization("bn254_g1_mul_batch: need 64 bytes of point and 32 of scalar per item"));
+        }
+        let count = points.len() / 64;
+        let mut out = vec![0u8; points.len()];
+        let mut st = vec![0u8; count];
+        // SAFETY: as above.
+        let status = unsafe { sys::b200zk_bn254_g1_mul_batch(self.ctx.as_ptr(), points.as_ptr(), scalars.as_ptr(), count, out.as_mut_ptr(), st.as_mut_ptr()) };
+        check(self, status)?;
+        Ok((out, st.into_iter().map(ItemStatus::from_code).collect()))
+    }
+
+    /// Several ecPairing checks in one launch.  `checks[i]` is the precompile's calldata (k x 192 bytes).
+    /// Returns, per check, `Ok(true/false)` or the input error.
+    pub fn bn254_pairing_check_batch(&mut self, checks: &[&[u8]]) -> Result<Vec<Result<bool, ItemStatus>>, BackendError> {
+        let mut blob = Vec::new();
+        let mut offsets = Vec::with_capacity(checks.len().saturating_add(1));
+        offsets.push(0u32);
+        for cd in checks {
+            if cd.len() % 192 != 0 {
+                return Err(BackendError::serialization("bn254_pairing_check_batch: calldata must be a multiple of 192 bytes"));
+            }
+            blob.extend_from_slice(cd);
+            let pairs = u32::try_from(blob.len() / 192).map_err(|_| BackendError::serialization("bn254_pairing_check_batch: too many pairs"))?;
+            offsets.push(pairs);
+        }
+        let count = checks.len();
+        let mut res = vec![0u8; count];
+        let mut st = vec![0u8; count];
+        // SAFETY: `offsets` has count + 1 entries, `blob` holds offsets[count] pairs, outputs hold `count` bytes.
+        let status = unsafe {
+            sys::b200zk_bn254_pairing_check_batch(self.ctx.as_ptr(), blob.as_ptr(), offsets.as_ptr(), count, res.as_mut_ptr(), st.as_mut_ptr())
+        };
+        check(self, status)?;
+        Ok(res
+            .into_iter()
+            .zip(st)
+            .map(|(r, s)| match ItemStatus::from_code(s) {
+                ItemStatus::Ok | ItemStatus::OkIdentity => Ok(r == 1),
+                bad => Err(bad),
+            })
+            .collect())
+    }
+}
+
 impl Drop for B200zk {
     fn drop(&mut self) {
         // SAFETY: ctx came from b200zk_init and is dropped exactly once.
