@@ -10,6 +10,7 @@ use ethrex_crypto::{Crypto, CryptoError};
 
 use crate::ffi::{global, ItemStatus};
 
+#[derive(Debug, Default, Clone, Copy)]
 pub struct B200Crypto;
 
 fn device_error<E: std::fmt::Display>(e: E) -> CryptoError {
