@@ -277,7 +277,7 @@ def run_gpu(args):
                 "binding_roofline": {"bound": "fmaheavy pipe (IMAD.WIDE): 254-bit modular products", "peak_products_per_s": MODMUL_PEAK,
                                      "achieved_products_per_s": (adds * PE / (acc / 1e3)) if adds else None,
                                      "frac": (adds * PE / (acc / 1e3) / MODMUL_PEAK) if adds else None,
-                                     "ncu_sm__pipe_fmaheavy_cycles_active_pct": 92.3},
+                                     "ncu_sm__pipe_fmaheavy_cycles_active_pct": 91.1, "ncu_source": "profiles/r1h_prof_summary.md"},
                 "note": "integer-compute-bound kernel (n*13 XYZZ mixed additions of 9.06 product-equivalents: 6 products, one mul2, 2 squarings): the HBM fraction is small by "
                         "construction, see DESIGN.md section 4; kernel_ms is measured in the one-shot schedule (phases are not separable "
                         "in the chunk-pipelined one that `value` runs)"}
