@@ -76,8 +76,10 @@ def serialize_program_input(program_input) -> bytes:
 
 
 class B200Backend:
-    def __init__(self, ctx=None, circuit=None, prover_type: ProverType = ProverType.SP1):
-        self.ctx, self.circuit, self._prover_type = ctx, circuit, prover_type
+    def __init__(self, ctx=None, circuit=None, prover_type: ProverType = ProverType.SP1, verifier=None):
+        """verifier: an ethrex_b200.groth16.Groth16Verifier for the circuit's verifying key (optional; without it
+        `verify` answers like a backend built without its SDK's verifier)."""
+        self.ctx, self.circuit, self._prover_type, self.verifier = ctx, circuit, prover_type, verifier
 
     # ---- ProverBackend ----
     def prover_type(self) -> ProverType:
@@ -109,8 +111,12 @@ class B200Backend:
             raise B200Error.proving(e) from e
         return B200ProveOutput(self.prover_type(), proof, commitments)
 
-    def verify(self, proof: B200ProveOutput) -> None:
-        raise B200Error.verify_not_supported()
+    def verify(self, proof: B200ProveOutput, public_inputs=None) -> None:
+        """ProverBackend::verify (backend/mod.rs:116-117): Ok(()) or BackendError::Verification."""
+        if self.verifier is None or public_inputs is None:
+            raise B200Error.verify_not_supported()
+        if not self.verifier.verify(proof.proof, public_inputs):
+            raise B200Error.verification("Groth16 pairing check failed")
 
     def to_proof_bytes(self, proof: B200ProveOutput, proof_format: ProofFormat = ProofFormat.GROTH16) -> ProverOutput:
         if proof_format is not ProofFormat.GROTH16:

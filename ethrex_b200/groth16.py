@@ -99,6 +99,41 @@ class Groth16Prover:
         return A + B2 + Cpt
 
 
+class Groth16Verifier:
+    """Groth16 verification on the device, many proofs per launch: what `ProverBackend::verify` does off-chain
+    (/root/reference/crates/prover/src/backend/mod.rs:116-117) and what the on-chain verifier contracts compute
+    (/root/reference/crates/l2/contracts/src/l1/OnChainProposer.sol:365-388) --
+        e(-A, B) * e(alpha, beta) * e(IC_0 + sum x_i IC_i, gamma) * e(C, delta) == 1
+    through b200zk_bn254_pairing_check_batch; the public-input combination is a small G1 MSM through the host entry
+    point.  All points are EIP-196/197 byte strings."""
+    P_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+
+    def __init__(self, ctx, alpha_g1: bytes, beta_g2: bytes, gamma_g2: bytes, delta_g2: bytes, ic):
+        if len(alpha_g1) != 64 or any(len(x) != 128 for x in (beta_g2, gamma_g2, delta_g2)) or not ic or any(len(x) != 64 for x in ic):
+            raise ValueError("verifying-key element sizes do not match")
+        self.ctx, self.alpha_g1, self.beta_g2, self.gamma_g2, self.delta_g2, self.ic = ctx, alpha_g1, beta_g2, gamma_g2, delta_g2, list(ic)
+
+    def _neg(self, g1: bytes) -> bytes:
+        x, y = int.from_bytes(g1[:32], "big"), int.from_bytes(g1[32:], "big")
+        return g1 if (x == 0 and y == 0) else g1[:32] + ((self.P_MOD - y) % self.P_MOD).to_bytes(32, "big")
+
+    def calldata(self, proof: bytes, public_inputs) -> bytes:
+        if len(proof) != 256 or len(public_inputs) != len(self.ic) - 1:
+            raise ValueError("proof must be 256 bytes and carry one public input per IC point after the first")
+        scalars = (1).to_bytes(32, "big") + b"".join(int(x % R_MOD).to_bytes(32, "big") for x in public_inputs)
+        vk_x = self.ctx.g1_msm(b"".join(self.ic), scalars, len(self.ic), F.POINTS_BE | F.SCALARS_BE)
+        a, b, c = proof[:64], proof[64:192], proof[192:]
+        return self._neg(a) + b + self.alpha_g1 + self.beta_g2 + vk_x + self.gamma_g2 + c + self.delta_g2
+
+    def verify_batch(self, proofs, public_inputs):
+        """-> list of booleans; a proof with a malformed point (status != 0) is False."""
+        res, st = self.ctx.bn254_pairing_check_batch([self.calldata(p, x) for p, x in zip(proofs, public_inputs)])
+        return [bool(r) and s == 0 for r, s in zip(res, st)]
+
+    def verify(self, proof: bytes, public_inputs) -> bool:
+        return self.verify_batch([proof], [public_inputs])[0]
+
+
 @dataclass
 class ProvingKey:
     """Resident (precomputed) proving-key columns: handles into the context + the chain scalars that define them."""

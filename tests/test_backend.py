@@ -77,3 +77,40 @@ def test_groth16_pipeline_matches_oracle(ctx):
         assert backend.prove({"blocks": [9]}).proof != proof.proof
     finally:
         circuit.close()
+
+
+def test_groth16_verifier_host_logic_without_a_gpu():
+    """Groth16Verifier's host side (negating A, the public-input combination, the pair order) against the toy
+    instance's own verifier calldata, with the MSM call served by the oracle; and the Verification error path of
+    B200Backend.verify with a stub verifier.  The device half runs in test_gpu_parity.py."""
+    from ethrex_b200.backend import B200ProveOutput
+    from ethrex_b200.groth16 import Groth16Verifier
+    from groth16_toy import ToyGroth16, _g1
+
+    class OracleMsm:
+        def g1_msm(self, pts, sc, n, flags):
+            acc = None
+            for i in range(n):
+                acc = pyref.g1_add(acc, pyref.g1_mul(int.from_bytes(sc[32 * i:32 * i + 32], "big"), pyref.g1_from_be(pts[64 * i:64 * i + 64])))
+            return pyref.g1_to_be(acc)
+
+    toy = ToyGroth16(3)
+    ver = Groth16Verifier(OracleMsm(), toy.vk_alpha_g1, toy.vk_beta_g2, toy.vk_gamma_g2, toy.vk_delta_g2, [_g1(s) for s in toy.ic])
+    for x in (0, 12345, pyref.R - 1):
+        proof = toy.expected_proof(toy.assign(x))
+        assert ver.calldata(proof, [x]) == toy.verifier_calldata(proof, x)
+    with pytest.raises(ValueError):
+        ver.calldata(proof[:255], [1])
+
+    class Stub:
+        def __init__(self, answer): self.answer = answer
+        def verify(self, proof, public_inputs): return self.answer
+
+    out = B200ProveOutput(ProverType.SP1, bytes(256), {})
+    B200Backend(None, verifier=Stub(True)).verify(out, [1])
+    with pytest.raises(eb.B200Error) as e:
+        B200Backend(None, verifier=Stub(False)).verify(out, [1])
+    assert e.value.kind == "Verification" and str(e.value).startswith("Verification error")
+    with pytest.raises(eb.B200Error) as e:
+        B200Backend(None).verify(out, [1])
+    assert e.value.kind == "NotImplemented"

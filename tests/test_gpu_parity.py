@@ -787,3 +787,37 @@ def test_msm_entry_points_report_the_identity_as_status_1(ctx):
     assert F.lib.b200zk_g1_msm_resident(ctx._h, h, five + rm5, 2, eb.SCALARS_BE, out) == 1
     assert F.lib.b200zk_g1_msm_resident(ctx._h, h, five + one, 2, eb.SCALARS_BE, out) == 0
     ctx.bases_free(h)
+
+
+@pytest.mark.gpu
+def test_groth16_verifier_batch_on_the_gpu(ctx):
+    """Groth16Verifier (what ProverBackend::verify / the on-chain verifier compute): proofs from the GPU prover for
+    several public inputs verify in one batch; a wrong public input, a tampered proof and a proof with a point off
+    the curve do not.  B200Backend.verify maps the outcome to Ok / BackendError::Verification."""
+    from ethrex_b200.backend import B200Backend, B200ProveOutput, ProverType
+    from ethrex_b200.groth16 import Groth16Prover, Groth16Verifier
+    from groth16_toy import N_PUBLIC, ToyGroth16, _g1
+    toy = ToyGroth16(4)
+    prover = Groth16Prover(ctx, 4, toy.a_g1, toy.b_g1, toy.b_g2, toy.l_g1, toy.h_g1, N_PUBLIC)
+    ver = Groth16Verifier(ctx, toy.vk_alpha_g1, toy.vk_beta_g2, toy.vk_gamma_g2, toy.vk_delta_g2, [_g1(s) for s in toy.ic])
+    try:
+        xs = [3, 0, pyref.R - 1, 0xDEADBEEF]
+        proofs = []
+        for x in xs:
+            z = toy.assign(x)
+            proofs.append(prover.prove(z, *toy.evaluations(z)))
+        assert ver.verify_batch(proofs, [[x] for x in xs]) == [True] * 4
+        assert ver.verify_batch(proofs, [[x + 1] for x in xs]) == [False] * 4
+        assert ver.verify_batch([proofs[1], proofs[0]], [[xs[0]], [xs[1]]]) == [False, False]
+        off_curve = proofs[0][:63] + bytes([proofs[0][63] ^ 1]) + proofs[0][64:]
+        assert ver.verify(off_curve, [xs[0]]) is False
+        backend = B200Backend(ctx, verifier=ver)
+        out = B200ProveOutput(ProverType.SP1, proofs[2], {})
+        backend.verify(out, [xs[2]])
+        with pytest.raises(eb.B200Error) as e:
+            backend.verify(out, [xs[3]])
+        assert e.value.kind == "Verification"
+        with pytest.raises(eb.B200Error):
+            B200Backend(ctx).verify(out, [xs[2]])  # no verifier: "Verify not implemented for this backend"
+    finally:
+        prover.close()
