@@ -44,6 +44,12 @@ pub trait WrapCircuit: Send + Sync {
     fn quotient_on_coset(&self, abc_coset: &mut [Vec<u8>; 3]) -> Result<Vec<u8>, BackendError>;
     /// Assemble (A, B, C) with the blinding terms and the verifier's byte order.
     fn assemble(&self, commitments: &Groth16Commitments) -> Result<Vec<u8>, BackendError>;
+    /// The ecpairing calldata of the Groth16 verification equation for `proof`
+    /// (`-A | B | alpha | beta | IC(public inputs) | gamma | C | delta`, 4 x 192 bytes), when the SDK exposes its
+    /// verifying key; `None` makes `verify` answer "not implemented", like the reference's default.
+    fn verifier_calldata(&self, _proof: &[u8]) -> Option<Vec<u8>> {
+        None
+    }
 }
 
 /// The five commitments of a Groth16 proof before blinding, EIP-196/197 encoded.
@@ -133,8 +139,20 @@ impl ProverBackend for B200Backend {
         }
     }
 
-    fn verify(&self, _proof: &Self::ProofOutput) -> Result<(), BackendError> {
-        Err(BackendError::verify_not_supported())
+    /// The pairing check of the Groth16 verification equation, on the device (`b200zk_bn254_pairing_check_batch`).
+    fn verify(&self, proof: &Self::ProofOutput) -> Result<(), BackendError> {
+        let calldata = self
+            .circuit
+            .as_ref()
+            .and_then(|c| c.verifier_calldata(&proof.proof))
+            .ok_or_else(BackendError::verify_not_supported)?;
+        let mut gpu = ffi::global()?.lock().map_err(|e| BackendError::verification(e.to_string()))?;
+        match gpu.bn254_pairing_check_batch(&[calldata.as_slice()])?.first() {
+            Some(Ok(true)) => Ok(()),
+            Some(Ok(false)) => Err(BackendError::verification("Groth16 pairing check failed")),
+            Some(Err(status)) => Err(BackendError::verification(format!("malformed proof point: {status:?}"))),
+            None => Err(BackendError::verification("b200zk returned no result")),
+        }
     }
 
     fn to_proof_bytes(&self, proof: Self::ProofOutput, _format: ProofFormat) -> Result<ProverOutput, BackendError> {
