@@ -790,6 +790,28 @@ def test_msm_entry_points_report_the_identity_as_status_1(ctx):
 
 
 @pytest.mark.gpu
+def test_groth16_golden_fixture(ctx):
+    """tests/golden/groth16_toy.json (made by make_groth16_golden.py on the CPU oracle): the GPU prover reproduces
+    the committed proof bytes, and the committed verifier calldata passes the GPU pairing check."""
+    import json
+    from ethrex_b200.groth16 import Groth16Prover
+    from groth16_toy import N_PUBLIC, ToyGroth16
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "groth16_toy.json")))
+    for inst in gold["instances"]:
+        toy = ToyGroth16(inst["log_n"])
+        prover = Groth16Prover(ctx, inst["log_n"], toy.a_g1, toy.b_g1, toy.b_g2, toy.l_g1, toy.h_g1, N_PUBLIC)
+        try:
+            for case in inst["cases"]:
+                x = int(case["public_input"], 16)
+                z = toy.assign(x)
+                assert prover.prove(z, *toy.evaluations(z)).hex() == case["proof"]
+            res, st = ctx.bn254_pairing_check_batch([bytes.fromhex(c["verifier_calldata"]) for c in inst["cases"]])
+            assert st == [0] * len(res) and res == [1] * len(res)
+        finally:
+            prover.close()
+
+
+@pytest.mark.gpu
 def test_groth16_verifier_batch_on_the_gpu(ctx):
     """Groth16Verifier (what ProverBackend::verify / the on-chain verifier compute): proofs from the GPU prover for
     several public inputs verify in one batch; a wrong public input, a tampered proof and a proof with a point off

@@ -225,3 +225,18 @@ def test_toy_groth16_instance_is_sound_under_the_kat_pinned_pairing():
     assert not tw.pairing_check(_pairs(toy.verifier_calldata(proof, x + 1)))
     bad = proof[:192] + o.g1_to_be(o.g1_add(o.g1_from_be(proof[192:256]), o.G1_GEN))
     assert not tw.pairing_check(_pairs(toy.verifier_calldata(bad, x)))
+
+
+def test_groth16_golden_fixture_is_current():
+    """tests/golden/groth16_toy.json matches what the toy instance produces today, and its verifier calldata passes the
+    tower pairing (the GPU side of the same fixture: test_gpu_parity.py::test_groth16_golden_fixture)."""
+    import pyref_tower as tw
+    from groth16_toy import ToyGroth16
+    gold = _json.load(open(os.path.join(GOLD, "groth16_toy.json")))
+    inst = gold["instances"][0]
+    toy = ToyGroth16(inst["log_n"])
+    for case in inst["cases"]:
+        x = int(case["public_input"], 16)
+        proof = toy.expected_proof(toy.assign(x))
+        assert proof.hex() == case["proof"] and toy.verifier_calldata(proof, x).hex() == case["verifier_calldata"]
+    assert tw.pairing_check(_pairs(bytes.fromhex(inst["cases"][0]["verifier_calldata"])))
