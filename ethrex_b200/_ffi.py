@@ -23,9 +23,17 @@ NTT_INVERSE = 1 << 4
 NTT_COSET = 1 << 5
 NTT_CANONICAL = 1 << 6
 NTT_BE = 1 << 7
+G16_INPUTS_DEVICE = 1 << 8
+G16_H_COEFFS = 1 << 9
 
 _vp, _sz, _u32, _u64, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
 _ctx = C.c_void_p
+
+
+class Groth16Pk(C.Structure):
+    """struct b200zk_groth16_pk (include/b200zk.h): columns 0..4 = A_g1, B_g1, B_g2, L_g1, H_g1"""
+    _fields_ = [("log_n", C.c_uint32), ("reserved", C.c_uint32), ("handle", C.c_uint64 * 5), ("count", C.c_uint64 * 5), ("offset", C.c_uint64 * 5)]
+
 
 # name -> (restype, argtypes); every symbol include/b200zk.h declares
 SIGNATURES = {
@@ -55,6 +63,11 @@ SIGNATURES = {
     "b200zk_g1_msm_device_async": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g2_msm_device_async": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_fr_ntt_device": (_int, [_ctx, _vp, _u32, _u32, _vp, _vp]),
+    "b200zk_set_ntt_root": (_int, [_ctx, _vp]),
+    "b200zk_ntt_root_preset": (_int, [_int, _vp]),
+    "b200zk_groth16_commit": (_int, [_ctx, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "b200zk_groth16_commit_partial": (_int, [_ctx, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "b200zk_groth16_fold": (_int, [_ctx, _vp, _sz, _vp, _vp, _vp]),
     "b200zk_g1_msm_partial_device": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g2_msm_partial_device": (_int, [_ctx, _vp, _vp, _sz, _u32, _vp, _vp]),
     "b200zk_g1_msm_partial_resident_device": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp, _vp]),

@@ -101,10 +101,11 @@ class B200Backend:
         if self.circuit is None:
             raise B200Error.not_implemented("b200 backend built without a wrap circuit: ProofFormat::Groth16 needs a zkVM SDK's proving key")
         try:
-            w, a, b, c = self.circuit.assign(serialized)
-            h = self.circuit.quotient(a, b, c)
-            commitments = self.circuit.commit(w, h, msm)
-            proof = self.circuit.assemble(commitments)
+            if msm is not None or not hasattr(self.circuit, "prove_device"):
+                proof, commitments = self.circuit.prove_separate(serialized, msm)
+            else:  # ONE C-ABI call per proof (b200zk_groth16_commit), like rust/ethrex-backend/src/b200.rs
+                proof, b_g1 = self.circuit.prove_device(serialized)
+                commitments = {"a_g1": proof[:64], "b_g2": proof[64:192], "c_g1": proof[192:], "b_g1": b_g1}
         except B200Error:
             raise
         except Exception as e:  # noqa: BLE001  (mirror of `.map_err(BackendError::proving)`)
@@ -138,6 +139,16 @@ class B200Backend:
         t0 = time.perf_counter()
         proof = self.prove(program_input, proof_format, msm)
         return proof, time.perf_counter() - t0
+
+
+def log_proved(payload_id: int, elapsed_s: float, logger=None) -> str:
+    """The reference's `--timed` log line (`Prover::poll_endpoints`, /root/reference/crates/prover/src/prover.rs:106-118):
+    fields `id`, `proving_time_s`, `proving_time_ms` and the message `Proved payload #<id> in <elapsed>`, kept
+    identical so that the reference's log scrapers (docs/l2 benchmarks) read this backend's timings unchanged."""
+    line = f"id={payload_id} proving_time_s={int(elapsed_s)} proving_time_ms={int(elapsed_s * 1000)} Proved payload #{payload_id} in {elapsed_s:.2f}s"
+    if logger is not None:
+        logger.info(line)
+    return line
 
 
 def proof_digest(proof: bytes) -> str:

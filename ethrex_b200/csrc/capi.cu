@@ -168,10 +168,12 @@ int b200zk_init(int device, b200zk_ctx** out) {
   int n = b200zk_device_count();
   if (n <= 0) return B200ZK_ERR_NO_DEVICE;
   if (device < 0 || device >= n) return B200ZK_ERR_INVALID_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200ZK_ERR_CUDA; }
   b200zk_ctx* ctx = new (std::nothrow) b200zk_ctx();
   if (!ctx) return B200ZK_ERR_OOM;
   ctx->device = device;
+  DeviceGuard guard(ctx);  // streams, events and every later allocation belong to `device`; the caller's current device is restored
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { cudaGetLastError(); delete ctx; return B200ZK_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -194,8 +196,12 @@ int b200zk_init(int device, b200zk_ctx** out) {
 
 void b200zk_destroy(b200zk_ctx* ctx) {
   if (!ctx) return;
+  int prev_device = -1;
+  if (cudaGetDevice(&prev_device) != cudaSuccess) { cudaGetLastError(); prev_device = -1; }
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  for (auto& b : ctx->ws_g16) if (b.p) cudaFree(b.p);
+  if (ctx->ws_zinv.p) cudaFree(ctx->ws_zinv.p);
   DevBuf* bufs[] = {&ctx->ws_hist, &ctx->ws_offsets, &ctx->ws_cursor, &ctx->ws_blocksums, &ctx->ws_idx, &ctx->ws_buckets, &ctx->ws_chunkS,
                     &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits, &ctx->ws_q0, &ctx->ws_q1, &ctx->ws_prefix, &ctx->ws_info, &ctx->ws_pairoff0, &ctx->ws_pairoff1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -209,42 +215,44 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   }
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
   if (ctx->stream_sort) cudaStreamDestroy(ctx->stream_sort);
-  for (auto& kv : ctx->twiddles) cudaFree(kv.second.d);
+  for (auto& kv : ctx->twiddles) { cudaFree(kv.second.d); if (kv.second.ready) cudaEventDestroy(kv.second.ready); }
   for (auto& kv : ctx->bases) cudaFree(kv.second.d);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  const int own = ctx->device;
   delete ctx;
+  if (prev_device >= 0 && prev_device != own) cudaSetDevice(prev_device);
 }
 
 const char* b200zk_last_error(const b200zk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int b200zk_synchronize(b200zk_ctx* ctx) {
+int b200zk_synchronize(b200zk_ctx* ctx) { b200zk::DeviceGuard guard(ctx);
   if (!ctx) return B200ZK_ERR_INVALID_ARG;
   B2_CUDA(ctx, cudaDeviceSynchronize());
   return B200ZK_OK;
 }
-int b200zk_set_msm_window(b200zk_ctx* ctx, uint32_t c) {
+int b200zk_set_msm_window(b200zk_ctx* ctx, uint32_t c) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (c && (c < 2 || c > 24))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm window must be 0 or 2..24");
   ctx->msm_window = c;
   return B200ZK_OK;
 }
-int b200zk_set_msm_chunks(b200zk_ctx* ctx, uint32_t chunks) {
+int b200zk_set_msm_chunks(b200zk_ctx* ctx, uint32_t chunks) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || chunks > 64) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm chunks must be 0 (automatic) .. 64");
   ctx->msm_chunks = chunks;
   return B200ZK_OK;
 }
-int b200zk_set_msm_pair_rounds(b200zk_ctx* ctx, int rounds) {
+int b200zk_set_msm_pair_rounds(b200zk_ctx* ctx, int rounds) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || rounds > 4) return fail(ctx, B200ZK_ERR_INVALID_ARG, "pair rounds must be <= 4 (negative = automatic)");
   ctx->msm_pair_rounds = rounds < 0 ? -1 : rounds;
   return B200ZK_OK;
 }
-int b200zk_set_profiling(b200zk_ctx* ctx, int enabled) {
+int b200zk_set_profiling(b200zk_ctx* ctx, int enabled) { b200zk::DeviceGuard guard(ctx);
   if (!ctx) return B200ZK_ERR_INVALID_ARG;
   ctx->profiling = enabled != 0;
   return B200ZK_OK;
 }
-int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]) {
+int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !out_ms) return fail(ctx, B200ZK_ERR_INVALID_ARG, "phase_ms: null argument");
   if (!ctx->profiling) return fail(ctx, B200ZK_ERR_INVALID_ARG, "profiling is off");
   B2_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
@@ -252,10 +260,10 @@ int b200zk_last_msm_phase_ms(b200zk_ctx* ctx, float out_ms[6]) {
   return B200ZK_OK;
 }
 
-int b200zk_g1_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t out[64]) { return msm_host<false>(ctx, points, scalars, n, flags, out); }
-int b200zk_g2_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t out[128]) { return msm_host<true>(ctx, points, scalars, n, flags, out); }
+int b200zk_g1_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t out[64]) { b200zk::DeviceGuard guard(ctx); return msm_host<false>(ctx, points, scalars, n, flags, out); }
+int b200zk_g2_msm(b200zk_ctx* ctx, const void* points, const void* scalars, size_t n, uint32_t flags, uint8_t out[128]) { b200zk::DeviceGuard guard(ctx); return msm_host<true>(ctx, points, scalars, n, flags, out); }
 
-int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen) {
+int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !data) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: null argument");
   if (log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: log_n > 28");
   const size_t bytes = ((size_t)1 << log_n) * 32;
@@ -268,14 +276,14 @@ int b200zk_fr_ntt(b200zk_ctx* ctx, void* data, uint32_t log_n, uint32_t flags, c
   return B200ZK_OK;
 }
 
-int b200zk_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { return bases_upload<false>(ctx, points, n, flags, handle); }
-int b200zk_g2_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { return bases_upload<true>(ctx, points, n, flags, handle); }
-int b200zk_g1_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) { return bases_from_device<false>(ctx, d_points, n, stream, handle); }
-int b200zk_g2_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) { return bases_from_device<true>(ctx, d_points, n, stream, handle); }
-int b200zk_g1_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[64]) { return msm_resident_device<false>(ctx, handle, d_scalars, n, flags, stream, out); }
-int b200zk_g2_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[128]) { return msm_resident_device<true>(ctx, handle, d_scalars, n, flags, stream, out); }
+int b200zk_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { b200zk::DeviceGuard guard(ctx); return bases_upload<false>(ctx, points, n, flags, handle); }
+int b200zk_g2_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle) { b200zk::DeviceGuard guard(ctx); return bases_upload<true>(ctx, points, n, flags, handle); }
+int b200zk_g1_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) { b200zk::DeviceGuard guard(ctx); return bases_from_device<false>(ctx, d_points, n, stream, handle); }
+int b200zk_g2_bases_from_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* stream, uint64_t* handle) { b200zk::DeviceGuard guard(ctx); return bases_from_device<true>(ctx, d_points, n, stream, handle); }
+int b200zk_g1_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[64]) { b200zk::DeviceGuard guard(ctx); return msm_resident_device<false>(ctx, handle, d_scalars, n, flags, stream, out); }
+int b200zk_g2_msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[128]) { b200zk::DeviceGuard guard(ctx); return msm_resident_device<true>(ctx, handle, d_scalars, n, flags, stream, out); }
 
-int b200zk_bases_precompute(b200zk_ctx* ctx, uint64_t handle, uint32_t window_bits) {
+int b200zk_bases_precompute(b200zk_ctx* ctx, uint64_t handle, uint32_t window_bits) { b200zk::DeviceGuard guard(ctx);
   if (!ctx) return B200ZK_ERR_INVALID_ARG;
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end()) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_precompute: unknown handle");
@@ -297,7 +305,7 @@ int b200zk_bases_precompute(b200zk_ctx* ctx, uint64_t handle, uint32_t window_bi
   return B200ZK_OK;
 }
 
-int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle) {
+int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle) { b200zk::DeviceGuard guard(ctx);
   if (!ctx) return B200ZK_ERR_INVALID_ARG;
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end()) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_free: unknown handle");
@@ -306,44 +314,58 @@ int b200zk_bases_free(b200zk_ctx* ctx, uint64_t handle) {
   ctx->bases.erase(it);
   return B200ZK_OK;
 }
-int b200zk_g1_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t out[64]) { return msm_resident<false>(ctx, handle, scalars, n, flags, out); }
-int b200zk_g2_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t out[128]) { return msm_resident<true>(ctx, handle, scalars, n, flags, out); }
+int b200zk_g1_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t out[64]) { b200zk::DeviceGuard guard(ctx); return msm_resident<false>(ctx, handle, scalars, n, flags, out); }
+int b200zk_g2_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t out[128]) { b200zk::DeviceGuard guard(ctx); return msm_resident<true>(ctx, handle, scalars, n, flags, out); }
 
-int b200zk_g1_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[64]) { return msm_device<false>(ctx, d_points, d_scalars, n, flags, stream, out); }
-int b200zk_g2_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[128]) { return msm_device<true>(ctx, d_points, d_scalars, n, flags, stream, out); }
-int b200zk_g1_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_out64) {
+int b200zk_g1_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[64]) { b200zk::DeviceGuard guard(ctx); return msm_device<false>(ctx, d_points, d_scalars, n, flags, stream, out); }
+int b200zk_g2_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t out[128]) { b200zk::DeviceGuard guard(ctx); return msm_device<true>(ctx, d_points, d_scalars, n, flags, stream, out); }
+int b200zk_g1_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_out64) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_out64 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
   // the encoder appends a 4-byte infinity flag: route through ws_out, then copy the point only
   cudaStream_t st = pick_stream(ctx, stream);
   B2_TRY(ensure(ctx, ctx->ws_out, 256));
   B2_TRY(msm_device_async<false>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p));
-  B2_CUDA(ctx, cudaMemcpyAsync(d_out64, ctx->ws_out.p, 64, cudaMemcpyDeviceToDevice, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(d_out64, ctx->ws_out.p, 64 + 4, cudaMemcpyDeviceToDevice, st));  // point | u32 is_infinity
   return B200ZK_OK;
 }
-int b200zk_g2_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_out128) {
+int b200zk_g2_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_out128) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_out128 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   B2_TRY(ensure(ctx, ctx->ws_out, 256));
   B2_TRY(msm_device_async<true>(ctx, d_points, d_scalars, n, flags, st, ctx->ws_out.p));
-  B2_CUDA(ctx, cudaMemcpyAsync(d_out128, ctx->ws_out.p, 128, cudaMemcpyDeviceToDevice, st));
+  B2_CUDA(ctx, cudaMemcpyAsync(d_out128, ctx->ws_out.p, 128 + 4, cudaMemcpyDeviceToDevice, st));  // point | u32 is_infinity
   return B200ZK_OK;
 }
-int b200zk_fr_ntt_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, void* stream) {
+int b200zk_fr_ntt_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, void* stream) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_data) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: null argument");
   return ntt_run(ctx, d_data, log_n, flags, coset_gen, pick_stream(ctx, stream));
 }
 
-int b200zk_g1_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) {
+int b200zk_set_ntt_root(b200zk_ctx* ctx, const uint8_t* root_le) {
+  if (!ctx) return B200ZK_ERR_INVALID_ARG;
+  DeviceGuard guard(ctx);
+  return ntt_set_root(ctx, root_le);
+}
+int b200zk_ntt_root_preset(int preset, uint8_t root_le_out[32]) {
+  // canonical little-endian bytes; values recomputed in tests/test_oracle.py from 5^((r-1)/2^28) and 7^((r-1)/2^28)
+  static const uint32_t kArk[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+  static const uint32_t kHalo2[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du, 0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+  if (!root_le_out || (preset != 0 && preset != 1)) return B200ZK_ERR_INVALID_ARG;
+  memcpy(root_le_out, preset ? kHalo2 : kArk, 32);
+  return B200ZK_OK;
+}
+
+int b200zk_g1_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial128 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial: null argument");
   if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
   return msm_run_g1(ctx, d_points, d_scalars, n, flags, pick_stream(ctx, stream), d_partial128);
 }
-int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
+int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial256 || ((!d_points || !d_scalars) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial: null argument");
   if (flags & B200ZK_POINTS_BE) return fail(ctx, B200ZK_ERR_INVALID_ARG, "device entry points take native points");
   return msm_run_g2(ctx, d_points, d_scalars, n, flags, pick_stream(ctx, stream), d_partial256);
 }
-int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) {
+int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial128 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
@@ -351,32 +373,33 @@ int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, cons
   return msm_run_g1(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n);
 }
 // host (pinned) scalars: their upload is chunk-pipelined with the accumulation; the partial stays on the device
-int b200zk_g1_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) {
+int b200zk_g1_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial128 || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g1(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n, scalars);
 }
-int b200zk_g2_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
+int b200zk_g2_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial256 || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end() || !it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g2(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial256, it->second.table_c, it->second.n, scalars);
 }
-int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) {
+int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial256 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
   if (it == ctx->bases.end() || !it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g2(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial256, it->second.table_c, it->second.n);
 }
-int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[64]) { return fold_partials<false>(ctx, d_partials, count, flags, stream, out); }
-int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[128]) { return fold_partials<true>(ctx, d_partials, count, flags, stream, out); }
+int b200zk_g1_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[64]) { b200zk::DeviceGuard guard(ctx); return fold_partials<false>(ctx, d_partials, count, flags, stream, out); }
+int b200zk_g2_fold_partials_device(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, void* stream, uint8_t out[128]) { b200zk::DeviceGuard guard(ctx); return fold_partials<true>(ctx, d_partials, count, flags, stream, out); }
 
 int b200zk_msm_multi_resident_device(b200zk_ctx* ctx, const uint64_t* handles, size_t count, const void* d_scalars, size_t n, uint32_t flags,
                                      void* stream, uint8_t* out, int* status) {
+  DeviceGuard guard(ctx);
   if (!ctx || (count && (!handles || !out || !status)) || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: null argument");
   if (!count) return B200ZK_OK;
   cudaStream_t st = pick_stream(ctx, stream);
@@ -413,15 +436,15 @@ int b200zk_msm_multi_resident_device(b200zk_ctx* ctx, const uint64_t* handles, s
   return B200ZK_OK;
 }
 
-int b200zk_bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, uint8_t* status) {
+int b200zk_bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, uint8_t* status) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (count && (!a || !b || !out || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_g1_add_batch: null argument");
   return bn254_g1_add_batch(ctx, a, b, count, out, status);
 }
-int b200zk_bn254_g1_mul_batch(b200zk_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t count, uint8_t* out, uint8_t* status) {
+int b200zk_bn254_g1_mul_batch(b200zk_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t count, uint8_t* out, uint8_t* status) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (count && (!points || !scalars || !out || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_g1_mul_batch: null argument");
   return bn254_g1_mul_batch(ctx, points, scalars, count, out, status);
 }
-int b200zk_bn254_pairing_check_batch(b200zk_ctx* ctx, const uint8_t* pairs, const uint32_t* pair_offsets, size_t count, uint8_t* result, uint8_t* status) {
+int b200zk_bn254_pairing_check_batch(b200zk_ctx* ctx, const uint8_t* pairs, const uint32_t* pair_offsets, size_t count, uint8_t* result, uint8_t* status) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (count && (!pair_offsets || !result || !status))) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_pairing_check_batch: null argument");
   if (count && pair_offsets[count] && !pairs) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bn254_pairing_check_batch: null pairs");
   return bn254_pairing_check_batch(ctx, pairs, pair_offsets, count, result, status);

@@ -21,6 +21,8 @@ struct TwiddleSet {   // per (log_n, direction): see ntt.cu
   void* d = nullptr;  // device allocation holding all tables
   size_t bytes = 0;
   uint32_t gen[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // coset tables: the generator they were built for
+  uint32_t root[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the 2^28-th root of unity the tables were built for (all zero = default)
+  cudaEvent_t ready = nullptr;  // recorded behind the build kernel: consumers on OTHER streams wait on it
 };
 
 struct SortSlot {  // one of the two sort workspaces of the chunk-pipelined MSM
@@ -49,6 +51,9 @@ struct b200zk_ctx {
   cudaEvent_t ev_in = nullptr;
   b200zk::SortSlot slot[2];
   b200zk::DevBuf ws_totals, ws_bitpart;
+  b200zk::DevBuf ws_g16[4];   // b200zk_groth16_commit: staged A/B/C evaluations (host inputs) and the 768-byte partial block
+  b200zk::DevBuf ws_zinv;     // 1/(5^n - 1) of the last quotient domain, canonical limbs (cached per log_n)
+  uint32_t zinv_log_n = 0xffffffffu;
   int msm_pair_rounds = -1;  // batched-affine pair-summing rounds before the XYZZ accumulation; <0 = automatic
   bool profiling = false;
   float phase_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -56,6 +61,10 @@ struct b200zk_ctx {
   // grow-only workspaces
   b200zk::DevBuf ws_hist, ws_offsets, ws_cursor, ws_blocksums, ws_idx, ws_buckets, ws_chunkS, ws_chunkV, ws_result,
       ws_points, ws_scalars, ws_ntt, ws_misc, ws_out, ws_segoff, ws_segbucket, ws_digits, ws_q0, ws_q1, ws_prefix, ws_info, ws_pairoff0, ws_pairoff1;
+  // 2^28-th primitive root of unity of Fr the NTT derives its domain generators from (canonical limbs).
+  // Default = ark-poly / gnark-crypto 5^((r-1)/2^28); halo2curves uses 7^((r-1)/2^28) (b200zk_set_ntt_root).
+  uint32_t ntt_root[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+  uint64_t ntt_root_id = 0;  // 0 = default; else a hash of ntt_root (part of the twiddle cache key)
   std::map<uint64_t, b200zk::TwiddleSet> twiddles;
   std::map<uint64_t, b200zk::BasesEntry> bases;
   uint64_t next_handle = 1;
@@ -96,6 +105,21 @@ inline int ensure(b200zk_ctx* ctx, DevBuf& b, size_t bytes) {
   b.cap = want;
   return B200ZK_OK;
 }
+
+// Every extern "C" entry runs on the context's device, whatever device is current on the calling thread (two
+// contexts in one process, or a torch current device that differs from the context's), and restores it on exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const b200zk_ctx* ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != ctx->device) { switched = cudaSetDevice(ctx->device) == cudaSuccess; if (!switched) cudaGetLastError(); }
+  }
+  ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 inline cudaStream_t pick_stream(b200zk_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
@@ -168,6 +192,15 @@ int msm_encode_g1(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_
 int msm_encode_g2(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, cudaStream_t st, void* d_out);
 int points_be_to_native(b200zk_ctx* ctx, const void* d_be, void* d_native, size_t n, bool g2, cudaStream_t st);
 int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st);
+int ntt_set_root(b200zk_ctx* ctx, const uint8_t* root_le);
+// out[i] = (a[i]*b[i] - c[i]) * zinv, zinv read from device memory (canonical limbs)
+int fr_quotient_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n, const uint32_t* d_zinv_canonical, cudaStream_t st);
+// *d_zinv = device pointer to 1/(5^(2^log_n) - 1) (canonical limbs), computed once per log_n on `st`
+int fr_coset_zinv_dev(b200zk_ctx* ctx, uint32_t log_n, cudaStream_t st, const uint32_t** d_zinv);
+int groth16_commit_partials(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, const void* witness, void* a_evals, void* b_evals, void* c_evals,
+                            uint32_t flags, cudaStream_t st, void* d_partials);
+// d_partials: count blocks of 768 B (A | B1 | B2 | L | H as XYZZ); d_out: proof A|B2|C (256 B) | B1 (64 B) | 4 x u32 is_infinity (A, B2, C, B1)
+int groth16_assemble_dev(b200zk_ctx* ctx, const void* d_partials, size_t count, cudaStream_t st, void* d_out);
 int bn254_g1_add_batch(b200zk_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t count, uint8_t* out, uint8_t* status);
 int bn254_g1_mul_batch(b200zk_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t count, uint8_t* out, uint8_t* status);
 int bn254_pairing_check_batch(b200zk_ctx* ctx, const uint8_t* pairs, const uint32_t* pair_offsets, size_t count, uint8_t* result, uint8_t* status);

@@ -701,6 +701,37 @@ __global__ void msm_encode(const void* __restrict__ partials, size_t count, bool
   *reinterpret_cast<uint32_t*>(out + 2 * FieldBytes<F>::value) = a.is_inf() ? 1u : 0u;  // right behind the point: read_result()
 }
 
+// ---- Groth16 assembly (b200zk_groth16_fold): fold `count` blocks of partial sums (768 B each: A | B1 | B2 | L | H in
+// XYZZ form, one block per rank), normalise and encode.  Four independent single-thread CTAs (each result costs one
+// Fermat inversion): 0 -> A, 1 -> B2, 2 -> C = L + H, 3 -> B1.  out: A (64) | B2 (128) | C (64) | B1 (64) | 4 x u32 is_infinity.
+__global__ void groth16_assemble(const uint8_t* __restrict__ partials, size_t count, uint8_t* __restrict__ out) {
+  if (threadIdx.x) return;
+  const uint32_t which = blockIdx.x;
+  uint32_t* inf = reinterpret_cast<uint32_t*>(out + 320);
+  if (which == 1) {
+    XYZZ<Fq2> acc = XYZZ<Fq2>::identity();
+    for (size_t k = 0; k < count; ++k) { XYZZ<Fq2> p = load_xyzz<Fq2>(partials + k * 768 + 256, 0); xyzz_add(acc, p); }
+    Affine<Fq2> a = xyzz_to_affine(acc);
+    encode_point(out + 64, a, false);
+    inf[1] = a.is_inf() ? 1u : 0u;
+    return;
+  }
+  XYZZ<Fq> acc = XYZZ<Fq>::identity();
+  const size_t off = which == 0 ? 0 : (which == 3 ? 128 : 512);
+  for (size_t k = 0; k < count; ++k) {
+    XYZZ<Fq> p = load_xyzz<Fq>(partials + k * 768 + off, 0);
+    xyzz_add(acc, p);
+    if (which == 2) { XYZZ<Fq> h = load_xyzz<Fq>(partials + k * 768 + 640, 0); xyzz_add(acc, h); }
+  }
+  Affine<Fq> a = xyzz_to_affine(acc);
+  encode_point(out + (which == 0 ? 0 : (which == 2 ? 192 : 256)), a, false);
+  inf[which == 0 ? 0 : (which == 2 ? 2 : 3)] = a.is_inf() ? 1u : 0u;
+}
+int groth16_assemble_dev(b200zk_ctx* ctx, const void* d_partials, size_t count, cudaStream_t st, void* d_out) {
+  B2_LAUNCH(ctx, groth16_assemble, 4, 32, 0, st, (const uint8_t*)d_partials, count, (uint8_t*)d_out);
+  return B200ZK_OK;
+}
+
 // ---- host orchestration ---------------------------------------------------------------------------------------
 static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
   if (ctx->profiling) cudaEventRecord(ctx->ev[k], st);

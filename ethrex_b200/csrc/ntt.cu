@@ -35,11 +35,14 @@ struct NttTables {
 };
 static constexpr uint32_t kDirectBits = 16;
 
-B2_D Fr fr_root_2_28() {  // 5^((r-1)/2^28), canonical 0x2a3c09f0a58a7e85...725b19f0
-  const uint32_t g[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+// The 2^28-th primitive root of unity the domain generators derive from is a PARAMETER: the
+// context default is ark-poly / gnark-crypto's 5^((r-1)/2^28) = 0x2a3c09f0a58a7e85...725b19f0; halo2curves (the
+// OpenVM wrap, /root/reference/crates/prover/src/backend/openvm.rs:52-56) uses 7^((r-1)/2^28) = 0x03ddb9f5...60c37c9c.
+struct RootArg { uint32_t v[8]; };  // canonical limbs
+B2_D Fr fr_root_2_28(const RootArg& g) {
   Fr c;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) c.v[i] = g[i];
+  for (int i = 0; i < 8; ++i) c.v[i] = g.v[i];
   return Fr::to_mont(c);
 }
 B2_D Fr fr_pow_u32(Fr b, uint32_t e) {
@@ -47,14 +50,14 @@ B2_D Fr fr_pow_u32(Fr b, uint32_t e) {
   while (e) { if (e & 1) acc = Fr::mul(acc, b); b = Fr::sqr(b); e >>= 1; }
   return acc;
 }
-B2_D Fr root_of_unity(uint32_t log_n) {
-  Fr w = fr_root_2_28();
+B2_D Fr root_of_unity(uint32_t log_n, const RootArg& g) {
+  Fr w = fr_root_2_28(g);
   for (uint32_t i = log_n; i < 28; ++i) w = Fr::sqr(w);
   return w;
 }
 
 // entries: [0, 4095) stage tables, then 2^lb lo, then 2^(k-lb) hi, then n^-1, then 2^16 direct, then 2^lb lo * n^-1
-__global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inverse, void* out, uint32_t n_lo, uint32_t n_hi) {
+__global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inverse, void* out, uint32_t n_lo, uint32_t n_hi, RootArg g) {
   uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_stage = (1u << kMaxStage) - 1;
   uint32_t total = n_stage + n_lo + n_hi + 1;
@@ -64,21 +67,21 @@ __global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inve
     uint32_t e = id - total - (1u << kDirectBits), N = 1u << log_n;
     if (inverse) e = (N - e) & (N - 1);
     Fr n = Fr::zero(); n.v[0] = N;
-    val = fr_pow_u32(root_of_unity(log_n), e);
+    val = fr_pow_u32(root_of_unity(log_n, g), e);
     if (inverse) val = Fr::mul(val, Fr::inv(Fr::to_mont(n)));
     store_fe<Fr>(out, id, val);
     return;
   }
   if (id >= total) {
     uint32_t x = id - total, D = 1u << kDirectBits;
-    val = fr_pow_u32(root_of_unity(kDirectBits), inverse ? (D - x) & (D - 1) : x);
+    val = fr_pow_u32(root_of_unity(kDirectBits, g), inverse ? (D - x) & (D - 1) : x);
     store_fe<Fr>(out, id, val);
     return;
   }
   if (id < n_stage) {
     uint32_t s = 32 - __clz(id + 1);           // id+1 in [2^(s-1), 2^s)
     uint32_t i = id + 1 - (1u << (s - 1));
-    Fr w = root_of_unity(s);
+    Fr w = root_of_unity(s, g);
     uint32_t e = inverse ? ((1u << s) - i) & ((1u << s) - 1) : i;
     val = fr_pow_u32(w, e);
   } else if (id < n_stage + n_lo + n_hi) {
@@ -86,12 +89,26 @@ __global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inve
     uint32_t e = x < n_lo ? x : (x - n_lo) << kLoBits;
     uint32_t N = 1u << log_n;  // log_n <= 28
     if (inverse) e = (N - e) & (N - 1);
-    val = fr_pow_u32(root_of_unity(log_n), e);
+    val = fr_pow_u32(root_of_unity(log_n, g), e);
   } else {
     Fr n = Fr::zero(); n.v[0] = 1u << log_n;
     val = inverse ? Fr::inv(Fr::to_mont(n)) : Fr::one();
   }
   store_fe<Fr>(out, id, val);
+}
+
+// flags[0] = 1 iff g^(2^28) == 1 and g^(2^27) != 1 (g canonical, < r)
+__global__ void ntt_check_root(RootArg g, uint32_t* flags) {
+  if (blockIdx.x || threadIdx.x) return;
+  Fr c, m = Fr::modulus(), t;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c.v[i] = g.v[i];
+  const bool in_range = detail::sub8(t.v, c.v, m.v) != 0;
+  Fr w = Fr::to_mont(c);
+  for (int i = 0; i < 27; ++i) w = Fr::sqr(w);
+  const bool half_is_one = (w == Fr::one());
+  w = Fr::sqr(w);
+  flags[0] = (in_range && !half_is_one && w == Fr::one()) ? 1u : 0u;
 }
 
 struct PassArgs {
@@ -291,7 +308,7 @@ __global__ void __launch_bounds__(256) fr_convert(void* data, size_t n, int to_m
 
 // ---- host side ----------------------------------------------------------------------------------------------
 static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_t st, NttTables* out) {
-  const uint64_t key = (uint64_t)log_n | ((uint64_t)inverse << 8);
+  const uint64_t key = ((uint64_t)log_n | ((uint64_t)inverse << 8)) ^ (ctx->ntt_root_id << 9);  // root id 0 (default) keeps the plain key
   const uint32_t n_stage = (1u << kMaxStage) - 1;
   const uint32_t lb = log_n < (uint32_t)kLoBits ? log_n : (uint32_t)kLoBits;
   const uint32_t n_lo = 1u << lb, n_hi = log_n > (uint32_t)kLoBits ? 1u << (log_n - kLoBits) : 1u;
@@ -301,9 +318,17 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
     ts.bytes = (size_t)(n_stage + n_lo + n_hi + 1 + (1u << kDirectBits) + n_lo) * 32;
     B2_CUDA(ctx, cudaMalloc(&ts.d, ts.bytes));
     uint32_t total = n_stage + n_lo + n_hi + 1 + (1u << kDirectBits) + n_lo;
-    B2_LAUNCH(ctx, ntt_build_tables, (total + 127) / 128, 128, 0, st, log_n, inverse ? 1 : 0, ts.d, n_lo, n_hi);
+    RootArg g;
+    memcpy(g.v, ctx->ntt_root, 32);
+    memcpy(ts.root, ctx->ntt_root, 32);
+    B2_LAUNCH(ctx, ntt_build_tables, (total + 127) / 128, 128, 0, st, log_n, inverse ? 1 : 0, ts.d, n_lo, n_hi, g);
+    // a later transform of this size on ANOTHER stream must not read half-built tables
+    if (cudaEventCreateWithFlags(&ts.ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ts.ready, st); else { cudaGetLastError(); ts.ready = nullptr; B2_CUDA(ctx, cudaStreamSynchronize(st)); }
     it = ctx->twiddles.emplace(key, ts).first;
+  } else if (memcmp(it->second.root, ctx->ntt_root, 32) != 0) {
+    return fail(ctx, B200ZK_ERR_CUDA, "ntt: twiddle cache key collision between two roots of unity");
   }
+  if (it->second.ready) B2_CUDA(ctx, cudaStreamWaitEvent(st, it->second.ready, 0));
   const uint4* base = (const uint4*)it->second.d;
   out->stage = base;
   out->lo = base + 2 * (size_t)n_stage;
@@ -369,6 +394,26 @@ static int launch_pass(b200zk_ctx* ctx, const PassArgs& a, cudaStream_t st) {
   return B200ZK_OK;
 }
 
+// root_le: canonical little-endian limbs of a primitive 2^28-th root of unity of Fr, or nullptr for the default
+int ntt_set_root(b200zk_ctx* ctx, const uint8_t* root_le) {
+  static const uint32_t kDefault[8] = {0x725b19f0u, 0x9bd61b6eu, 0x41112ed4u, 0x402d111eu, 0x8ef62abcu, 0x00e0a7ebu, 0xa58a7e85u, 0x2a3c09f0u};
+  if (!root_le || memcmp(root_le, kDefault, 32) == 0) { memcpy(ctx->ntt_root, kDefault, 32); ctx->ntt_root_id = 0; return B200ZK_OK; }
+  RootArg g;
+  memcpy(g.v, root_le, 32);
+  B2_TRY(ensure(ctx, ctx->ws_result, 256));
+  cudaStream_t st = ctx->stream;
+  B2_LAUNCH(ctx, ntt_check_root, 1, 32, 0, st, g, (uint32_t*)ctx->ws_result.p);
+  B2_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 3584, ctx->ws_result.p, 4, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(ctx, cudaStreamSynchronize(st));
+  uint32_t ok; memcpy(&ok, ctx->h_pinned + 3584, 4);
+  if (!ok) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt root: not a primitive 2^28-th root of unity of Fr");
+  memcpy(ctx->ntt_root, g.v, 32);
+  uint64_t id = 0xcbf29ce484222325ull;
+  for (int i = 0; i < 8; ++i) id = (id ^ g.v[i]) * 0x100000001b3ull;
+  ctx->ntt_root_id = (id >> 10) | 1;  // non-zero, fits under the key's tag bit after the << 9
+  return B200ZK_OK;
+}
+
 int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st) {
   if (log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: log_n > 28 (two-adicity of Fr)");
   if ((uintptr_t)d_data & 15) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: the device buffer must be 16-byte aligned");
@@ -396,6 +441,7 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
     if (it != ctx->twiddles.end() && memcmp(it->second.gen, h, 32) != 0) {  // 64-bit key collision: rebuild
       B2_CUDA(ctx, cudaDeviceSynchronize());
       cudaFree(it->second.d);
+      if (it->second.ready) cudaEventDestroy(it->second.ready);
       ctx->twiddles.erase(it);
       it = ctx->twiddles.end();
     }
@@ -409,8 +455,10 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
       uint8_t* base = (uint8_t*)ts.d;
       B2_LAUNCH(ctx, ntt_build_pow_tables, (n_lo + n_hi + 127) / 128, 128, 0, st, (const uint32_t*)base, inverse ? 1 : 0, inverse ? 1 : 0, log_n,
                 (void*)(base + 64), n_lo, (void*)(base + 64 + (size_t)n_lo * 32), n_hi);
+      if (cudaEventCreateWithFlags(&ts.ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ts.ready, st); else { cudaGetLastError(); ts.ready = nullptr; B2_CUDA(ctx, cudaStreamSynchronize(st)); }
       it = ctx->twiddles.emplace(key, ts).first;
     }
+    if (it->second.ready) B2_CUDA(ctx, cudaStreamWaitEvent(st, it->second.ready, 0));
     uint8_t* base = (uint8_t*)it->second.d;
     c_lo = base + 64; c_hi = base + 64 + (size_t)n_lo * 32;
     // log_n == 0 has no pass to fuse into: scale the single element directly

@@ -51,6 +51,18 @@ __global__ void __launch_bounds__(256) fr_quotient(const void* a, const void* b,
   }
 }
 
+// zinv = 1 / (5^(2^log_n) - 1), canonical limbs: the inverse of the vanishing polynomial of the size-2^log_n domain on the
+// coset 5 * <w> (a constant there).  One thread, once per domain size.
+__global__ void fr_coset_zinv(uint32_t log_n, uint32_t* out_canonical) {
+  if (blockIdx.x || threadIdx.x) return;
+  Fr g = Fr::zero(); g.v[0] = 5;
+  g = Fr::to_mont(g);
+  for (uint32_t i = 0; i < log_n; ++i) g = Fr::sqr(g);
+  Fr z = Fr::from_mont(Fr::inv(Fr::sub(g, Fr::one())));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out_canonical[k] = z.v[k];
+}
+
 // ---- splitmix64 counter generator (identical to oracle/pyref.py rand_fr and the C++ oracle) -----------------------
 B2_D uint64_t splitmix64(uint64_t& st) {
   st += 0x9E3779B97F4A7C15ull;
@@ -157,6 +169,21 @@ static unsigned egrid(b200zk_ctx* ctx, size_t n, unsigned block) {
   return (unsigned)(g < cap ? (g ? g : 1) : cap);
 }
 
+int fr_quotient_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n, const uint32_t* d_zinv_canonical, cudaStream_t st) {
+  if (!n) return B200ZK_OK;
+  B2_LAUNCH(ctx, fr_quotient, egrid(ctx, n, 256), 256, 0, st, d_a, d_b, d_c, d_out, n, d_zinv_canonical);
+  return B200ZK_OK;
+}
+int fr_coset_zinv_dev(b200zk_ctx* ctx, uint32_t log_n, cudaStream_t st, const uint32_t** d_zinv) {
+  B2_TRY(ensure(ctx, ctx->ws_zinv, 64));
+  if (ctx->zinv_log_n != log_n) {
+    B2_LAUNCH(ctx, fr_coset_zinv, 1, 32, 0, st, log_n, (uint32_t*)ctx->ws_zinv.p);
+    B2_CUDA(ctx, cudaStreamSynchronize(st));  // one-off per domain size: later calls on other streams may read it unordered
+    ctx->zinv_log_n = log_n;
+  }
+  *d_zinv = (const uint32_t*)ctx->ws_zinv.p;
+  return B200ZK_OK;
+}
 int points_be_to_native(b200zk_ctx* ctx, const void* d_be, void* d_native, size_t n, bool g2, cudaStream_t st) {
   B2_TRY(ensure(ctx, ctx->ws_out, 256));
   unsigned long long* status = (unsigned long long*)((uint8_t*)ctx->ws_out.p + 192);
@@ -179,7 +206,7 @@ using namespace b200zk;
 
 extern "C" {
 
-int b200zk_field_to_mont_device(b200zk_ctx* ctx, void* d, size_t n, int which, void* stream) {
+int b200zk_field_to_mont_device(b200zk_ctx* ctx, void* d, size_t n, int which, void* stream) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (!d && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "field_to_mont: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   if (!n) return B200ZK_OK;
@@ -187,7 +214,7 @@ int b200zk_field_to_mont_device(b200zk_ctx* ctx, void* d, size_t n, int which, v
   else B2_LAUNCH(ctx, field_convert<Fr>, egrid(ctx, n, 256), 256, 0, st, d, n, 1);
   return B200ZK_OK;
 }
-int b200zk_field_from_mont_device(b200zk_ctx* ctx, void* d, size_t n, int which, void* stream) {
+int b200zk_field_from_mont_device(b200zk_ctx* ctx, void* d, size_t n, int which, void* stream) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (!d && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "field_from_mont: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   if (!n) return B200ZK_OK;
@@ -195,7 +222,7 @@ int b200zk_field_from_mont_device(b200zk_ctx* ctx, void* d, size_t n, int which,
   else B2_LAUNCH(ctx, field_convert<Fr>, egrid(ctx, n, 256), 256, 0, st, d, n, 0);
   return B200ZK_OK;
 }
-int b200zk_field_mul_device(b200zk_ctx* ctx, const void* a, const void* b, void* out, size_t n, int which, uint32_t repeat, void* stream) {
+int b200zk_field_mul_device(b200zk_ctx* ctx, const void* a, const void* b, void* out, size_t n, int which, uint32_t repeat, void* stream) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || ((!a || !b || !out) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "field_mul: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   if (!n) return B200ZK_OK;
@@ -210,7 +237,7 @@ int b200zk_field_mul_device(b200zk_ctx* ctx, const void* a, const void* b, void*
   else return fail(ctx, B200ZK_ERR_INVALID_ARG, "field_mul: which must be 0..3");
   return B200ZK_OK;
 }
-int b200zk_fr_quotient_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n, const uint8_t zinv[32], void* stream) {
+int b200zk_fr_quotient_device(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n, const uint8_t zinv[32], void* stream) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !zinv || ((!d_a || !d_b || !d_c || !d_out) && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "fr_quotient: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   if (!n) return B200ZK_OK;
@@ -221,7 +248,7 @@ int b200zk_fr_quotient_device(b200zk_ctx* ctx, const void* d_a, const void* d_b,
   B2_CUDA(ctx, cudaStreamSynchronize(st));  // staging buffers are reused by the next call
   return B200ZK_OK;
 }
-int b200zk_fr_random_device(b200zk_ctx* ctx, void* d_out, size_t n, uint64_t seed, uint64_t start, uint32_t flags, void* stream) {
+int b200zk_fr_random_device(b200zk_ctx* ctx, void* d_out, size_t n, uint64_t seed, uint64_t start, uint32_t flags, void* stream) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || (!d_out && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "fr_random: null argument");
   cudaStream_t st = pick_stream(ctx, stream);
   if (!n) return B200ZK_OK;
@@ -247,10 +274,10 @@ static int chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, co
   return B200ZK_OK;
 }
 extern "C" {
-int b200zk_g1_chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, const uint8_t k[32], const uint8_t d[32], void* stream) {
+int b200zk_g1_chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, const uint8_t k[32], const uint8_t d[32], void* stream) { b200zk::DeviceGuard guard(ctx);
   return chain_device<Fq>(ctx, d_out, start, n, k, d, stream);
 }
-int b200zk_g2_chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, const uint8_t k[32], const uint8_t d[32], void* stream) {
+int b200zk_g2_chain_device(b200zk_ctx* ctx, void* d_out, size_t start, size_t n, const uint8_t k[32], const uint8_t d[32], void* stream) { b200zk::DeviceGuard guard(ctx);
   return chain_device<Fq2>(ctx, d_out, start, n, k, d, stream);
 }
 
@@ -272,7 +299,7 @@ static int check_device(b200zk_ctx* ctx, const void* d_points, size_t n, void* s
   return B200ZK_OK;
 }
 extern "C" {
-int b200zk_g1_check_device(b200zk_ctx* ctx, const void* p, size_t n, void* stream, size_t* bad) { return check_device<Fq>(ctx, p, n, stream, bad); }
-int b200zk_g2_check_device(b200zk_ctx* ctx, const void* p, size_t n, void* stream, size_t* bad) { return check_device<Fq2>(ctx, p, n, stream, bad); }
+int b200zk_g1_check_device(b200zk_ctx* ctx, const void* p, size_t n, void* stream, size_t* bad) { b200zk::DeviceGuard guard(ctx); return check_device<Fq>(ctx, p, n, stream, bad); }
+int b200zk_g2_check_device(b200zk_ctx* ctx, const void* p, size_t n, void* stream, size_t* bad) { b200zk::DeviceGuard guard(ctx); return check_device<Fq2>(ctx, p, n, stream, bad); }
 
 }  // extern "C"

@@ -44,3 +44,24 @@ def msm_sharded(ctx, d_points, d_scalars, n_local: int, flags: int = 0, g2: bool
 def ntt_batch_assignment(num_polys: int, rank: int, world: int) -> list[int]:
     """Independent transforms (the 3+3+1 of a Groth16 quotient) are dealt round-robin: replicas, no collective."""
     return [i for i in range(num_polys) if i % world == rank]
+
+
+def quotient_dealt(ctx, log_n: int, a, b, c, zinv: int, rank: int, world: int, group=None):
+    """Groth16 quotient H = (A*B - C)/Z_H on `world` ranks: the three (iNTT, coset NTT) pairs are independent
+    transforms and are dealt round-robin (`ntt_batch_assignment`: replicas), each owner
+    broadcasts its coset evaluations (n x 32 bytes over NCCL / NVLink), then every rank does the cheap tail itself
+    (pointwise quotient + ONE coset iNTT) -- 2 + 1 transforms per rank instead of 7.  a, b, c: Montgomery device
+    tensors holding the evaluations on the domain; returns H's coefficients (in `a`) on every rank."""
+    import torch.distributed as dist
+    from . import _ffi as F
+    polys = (a, b, c)
+    for i in ntt_batch_assignment(3, rank, world):
+        ctx.fr_ntt_device(polys[i], log_n, F.NTT_INVERSE)
+        ctx.fr_ntt_device(polys[i], log_n, F.NTT_COSET)
+    if world > 1:
+        works = [dist.broadcast(polys[i], src=(i % world if group is None else dist.get_global_rank(group, i % world)), group=group, async_op=True) for i in range(3)]
+        for wk in works:
+            wk.wait()
+    ctx.fr_quotient_device(a, b, c, a, 1 << log_n, zinv)
+    ctx.fr_ntt_device(a, log_n, F.NTT_INVERSE | F.NTT_COSET)
+    return a

@@ -67,6 +67,10 @@ class Groth16Prover:
         self.h = {"a_g1": up1(a_g1, self.m, F.POINTS_BE), "b_g1": up1(b_g1, self.m, F.POINTS_BE), "b_g2": up2(b_g2, self.m, F.POINTS_BE),
                   "l_g1": up1(l_g1, self.m - n_public, F.POINTS_BE), "h_g1": up1(h_g1, self.n - 1, F.POINTS_BE)}
         self.zinv = coset_vanishing_inverse(log_n)
+        # struct b200zk_groth16_pk: whole columns on one GPU; L starts behind the public variables, H has n-1 points
+        self.pk = ctx.groth16_pk(log_n, [self.h[q] for q in ("a_g1", "b_g1", "b_g2", "l_g1", "h_g1")],
+                                 [self.m, self.m, self.m, self.m - n_public, self.n - 1], [0, 0, 0, n_public, 0])
+        self.b_g1 = None  # [B]1 of the last proof (what blinding would consume)
 
     def close(self):
         for h in self.h.values():
@@ -75,28 +79,18 @@ class Groth16Prover:
 
     def prove(self, z, a_evals, b_evals, c_evals) -> bytes:
         """z: the full assignment (integers mod r, z[0] = 1, then the public inputs, then the private variables);
-        a/b/c_evals: (A z), (B z), (C z) on the domain.  Returns A (64) | B (128) | C (64)."""
-        import numpy as np
-        import torch
-        ctx, n = self.ctx, self.n
+        a/b/c_evals: (A z), (B z), (C z) on the domain.  Returns A (64) | B (128) | C (64).
+        ONE call of the C ABI (b200zk_groth16_commit) with host buffers -- what rust/ethrex-backend/src/b200.rs does."""
+        if len(z) != self.m or any(len(e) != self.n for e in (a_evals, b_evals, c_evals)):
+            raise ValueError("assignment / evaluation vector sizes do not match the proving key")
+        r_mont = (1 << 256) % R_MOD
 
-        def dev(vals):
-            raw = b"".join(int(v % R_MOD).to_bytes(32, "little") for v in vals)
-            t = torch.from_numpy(np.frombuffer(raw, dtype=np.int64).copy()).cuda()
-            ctx.field_to_mont_device(t, len(vals), 1)
-            return t
+        def mont(vals):  # host-side Montgomery form (the SDK's field code holds its vectors this way)
+            return b"".join(int(v % R_MOD * r_mont % R_MOD).to_bytes(32, "little") for v in vals)
 
-        a, b, c = dev(a_evals), dev(b_evals), dev(c_evals)
-        hq = quotient_on_device(ctx, self.log_n, a, b, c, self.zinv)
         zb = b"".join(int(v % R_MOD).to_bytes(32, "little") for v in z)
-        A = ctx.g1_msm_resident(self.h["a_g1"], zb, self.m)
-        B1 = ctx.g1_msm_resident(self.h["b_g1"], zb, self.m)  # noqa: F841  (blinding would use it; kept for the op count)
-        B2 = ctx.g2_msm_resident(self.h["b_g2"], zb, self.m)
-        L = ctx.g1_msm_resident(self.h["l_g1"], zb[32 * self.n_public:], self.m - self.n_public)
-        H = ctx.g1_msm_resident_device(self.h["h_g1"], hq, n - 1, F.SCALARS_MONT)
-        one = (1).to_bytes(32, "little")
-        Cpt = ctx.g1_msm(L + H, one + one, 2, F.POINTS_BE)
-        return A + B2 + Cpt
+        proof, self.b_g1 = self.ctx.groth16_commit(self.pk, zb, bytearray(mont(a_evals)), bytearray(mont(b_evals)), bytearray(mont(c_evals)))
+        return proof
 
 
 class Groth16Verifier:
@@ -113,22 +107,44 @@ class Groth16Verifier:
             raise ValueError("verifying-key element sizes do not match")
         self.ctx, self.alpha_g1, self.beta_g2, self.gamma_g2, self.delta_g2, self.ic = ctx, alpha_g1, beta_g2, gamma_g2, delta_g2, list(ic)
 
-    def _neg(self, g1: bytes) -> bytes:
+    def _neg(self, g1: bytes):
+        """-A for a CANONICAL encoding; None when a coordinate is >= p.  The levm ecpairing wrapper and the on-chain
+        verifier reject such an A (CoordinateExceedsFieldModulus, crates/vm/levm/src/precompiles.rs:801-820); reducing y
+        here first would turn (x, y + p) into a point that verifies -- proof malleability."""
         x, y = int.from_bytes(g1[:32], "big"), int.from_bytes(g1[32:], "big")
-        return g1 if (x == 0 and y == 0) else g1[:32] + ((self.P_MOD - y) % self.P_MOD).to_bytes(32, "big")
+        if x >= self.P_MOD or y >= self.P_MOD:
+            return None
+        return g1 if (x == 0 and y == 0) else g1[:32] + (self.P_MOD - y).to_bytes(32, "big")
 
-    def calldata(self, proof: bytes, public_inputs) -> bytes:
+    def calldata(self, proof: bytes, public_inputs):
+        """ecpairing calldata of the verification equation, or None when the proof / inputs are not canonically encoded
+        (a public input outside [0, r) is rejected, not reduced: x and x + r must not verify alike)."""
         if len(proof) != 256 or len(public_inputs) != len(self.ic) - 1:
             raise ValueError("proof must be 256 bytes and carry one public input per IC point after the first")
-        scalars = (1).to_bytes(32, "big") + b"".join(int(x % R_MOD).to_bytes(32, "big") for x in public_inputs)
-        vk_x = self.ctx.g1_msm(b"".join(self.ic), scalars, len(self.ic), F.POINTS_BE | F.SCALARS_BE)
+        if any((not isinstance(x, int)) or x < 0 or x >= R_MOD for x in public_inputs):
+            return None
         a, b, c = proof[:64], proof[64:192], proof[192:]
-        return self._neg(a) + b + self.alpha_g1 + self.beta_g2 + vk_x + self.gamma_g2 + c + self.delta_g2
+        neg_a = self._neg(a)
+        if neg_a is None:
+            return None
+        scalars = (1).to_bytes(32, "big") + b"".join(int(x).to_bytes(32, "big") for x in public_inputs)
+        vk_x = self.ctx.g1_msm(b"".join(self.ic), scalars, len(self.ic), F.POINTS_BE | F.SCALARS_BE)
+        return neg_a + b + self.alpha_g1 + self.beta_g2 + vk_x + self.gamma_g2 + c + self.delta_g2
 
     def verify_batch(self, proofs, public_inputs):
-        """-> list of booleans; a proof with a malformed point (status != 0) is False."""
-        res, st = self.ctx.bn254_pairing_check_batch([self.calldata(p, x) for p, x in zip(proofs, public_inputs)])
-        return [bool(r) and s == 0 for r, s in zip(res, st)]
+        """-> list of booleans; a proof with a malformed point (status != 0) or a non-canonical encoding is False."""
+        cds = [self.calldata(p, x) for p, x in zip(proofs, public_inputs)]
+        live = [cd for cd in cds if cd is not None]
+        res, st = self.ctx.bn254_pairing_check_batch(live) if live else ([], [])
+        it = iter(zip(res, st))
+        out = []
+        for cd in cds:
+            if cd is None:
+                out.append(False)
+            else:
+                r, s = next(it)
+                out.append(bool(r) and s == 0)
+        return out
 
     def verify(self, proof: bytes, public_inputs) -> bool:
         return self.verify_batch([proof], [public_inputs])[0]
@@ -195,8 +211,39 @@ class SyntheticWrapCircuit:
         """H coefficients (Montgomery) from the A,B,C evaluations; a is overwritten with H."""
         return quotient_on_device(self.ctx, self.log_n, a, b, c, self.zinv)
 
+    def pk_struct(self):
+        """struct b200zk_groth16_pk of THIS rank's shard: every column holds points [lo, hi) of its whole column, so the
+        first scalar a column multiplies is entry `lo` of the witness (A, B1, B2, L) or of the quotient (H).  The
+        synthetic circuit has no public inputs: L spans the whole witness like A."""
+        lo, m = self.lo, self.hi - self.lo
+        mh = max(0, min(self.hi, self.n - 1) - lo)  # H has n-1 points: the last rank's shard is one short
+        hd = self.pk.handles
+        return self.ctx.groth16_pk(self.log_n, [hd["a_g1"], hd["b_g1"], hd.get("b_g2", 0), hd["l_g1"], hd["h_g1"]], [m, m, m, m, mh], [lo] * 5)
+
+    def prove_device(self, serialized_input: bytes, group=None):
+        """-> (proof bytes A | B2 | C, [B]1 bytes).  One GPU: ONE C-ABI call (b200zk_groth16_commit) on device inputs.
+        Several GPUs: the quotient's NTTs are dealt across ranks (dist.quotient_dealt), every rank commits its shard of
+        the proving key (b200zk_groth16_commit_partial), ONE all_gather moves the 768-byte blocks and every rank folds."""
+        import torch
+        ctx = self.ctx
+        w, a, b, c = self.assign(serialized_input)
+        pk = self.pk_struct()
+        if "b_g2" not in self.pk.handles:
+            raise ValueError("the one-call path needs the G2 column")
+        if self.world == 1:
+            return ctx.groth16_commit(pk, w, a, b, c, F.G16_INPUTS_DEVICE)
+        import torch.distributed as dist
+        from .dist import quotient_dealt
+        h = quotient_dealt(ctx, self.log_n, a, b, c, self.zinv, self.rank, self.world, group)
+        block = torch.zeros(96, dtype=torch.int64, device=w.device)  # 768 bytes: A | B1 | B2 | L | H partial sums
+        ctx.groth16_commit_partial(pk, w, h, None, None, block, F.G16_INPUTS_DEVICE | F.G16_H_COEFFS)
+        gathered = torch.empty(96 * self.world, dtype=torch.int64, device=w.device)
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        return ctx.groth16_fold(gathered, self.world)
+
     def commit(self, w, h_coeffs, msm=None):
-        """The five MSMs.  `msm(name, scalars, n, flags)` lets the multi-GPU driver substitute a sharded MSM."""
+        """The five MSMs as separate calls (the pre-ABI-v2 path, kept as a cross-check of the one-call path and for the
+        `msm` hook).  `msm(name, scalars, n, flags)` lets a driver substitute its own MSM."""
         ctx, n = self.ctx, self.n
 
         def local(name, scalars, count, flags):
@@ -230,7 +277,14 @@ class SyntheticWrapCircuit:
         b2 = commitments.get("b_g2", bytes(128))
         return commitments["a_g1"] + b2 + c_pt
 
-    def prove(self, serialized_input: bytes, msm=None) -> bytes:
+    def prove_separate(self, serialized_input: bytes, msm=None):
+        """the pre-ABI-v2 sequence: quotient, five separately read-back MSMs, host-side assembly -> (proof, commitments)"""
         w, a, b, c = self.assign(serialized_input)
         h = self.quotient(a, b, c)
-        return self.assemble(self.commit(w, h, msm))
+        cm = self.commit(w, h, msm)
+        return self.assemble(cm), cm
+
+    def prove(self, serialized_input: bytes, msm=None) -> bytes:
+        if msm is not None or "b_g2" not in self.pk.handles:
+            return self.prove_separate(serialized_input, msm)[0]
+        return self.prove_device(serialized_input)[0]

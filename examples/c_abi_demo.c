@@ -8,7 +8,11 @@
  *   2. b200zk_g1_msm (big-endian points and scalars): 3*G + 4*G = 7*G; 5*G + (r-5)*G = identity (status 1)
  *   3. b200zk_bn254_pairing_check_batch: e(G1, G2) * e(-G1, G2) = 1 (EIP-197 generator), and e(G1,G2)^2 != 1
  *   4. b200zk_fr_ntt: forward then inverse of 2^10 canonical big-endian values returns the input; NTT(delta_0) = 1...1
- *   5. error convention: a coordinate >= p gives status 2 (CoordinateExceedsFieldModulus), (1,3) status 3 */
+ *   5. error convention: a coordinate >= p gives status 2 (CoordinateExceedsFieldModulus), (1,3) status 3
+ *   6. (with a fixture path as argv[1]) a REAL Groth16 instance through C only: the proving key is uploaded once
+ *      (b200zk_g{1,2}_bases_upload + b200zk_bases_precompute), then ONE call of b200zk_groth16_commit -- 7 NTTs, the
+ *      quotient, 4 G1 MSMs + 1 G2 MSM, C = L + H -- must return, byte for byte, the proof computed in the exponent
+ *      (tests/groth16_toy.py writes the fixture; layout in write_c_fixture()). */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,7 +33,20 @@ static int from_hex(const char* hex, uint8_t* out, size_t n) {
     printf("ok   %s\n", what);                                         \
   } while (0)
 
-int main(void) {
+static uint8_t* slurp(const char* path, size_t* len) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return NULL;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  uint8_t* buf = (uint8_t*)malloc((size_t)n);
+  if (buf && fread(buf, 1, (size_t)n, f) != (size_t)n) { free(buf); buf = NULL; }
+  fclose(f);
+  *len = (size_t)n;
+  return buf;
+}
+
+int main(int argc, char** argv) {
   b200zk_ctx* ctx = NULL;
   int rc = b200zk_init(0, &ctx);
   if (rc != B200ZK_OK) { fprintf(stderr, "b200zk_init: status %d (%s)\n", rc, b200zk_strerror(rc)); return 2; }
@@ -107,6 +124,51 @@ int main(void) {
   CHECK(rc == B200ZK_OK && sts[0] == B200ZK_ERR_NOT_IN_FIELD && sts[1] == B200ZK_ERR_NOT_ON_CURVE, "status 2 for x >= p, status 3 for a point off the curve");
   rc = b200zk_g1_msm(ctx, bad, ks, 1, B200ZK_POINTS_BE | B200ZK_SCALARS_BE, out);
   CHECK(rc == B200ZK_ERR_NOT_IN_FIELD, "host MSM rejects x >= p with status 2");
+
+  /* 6. Groth16 prove arithmetic in one call, against a proof computed in the exponent */
+  if (argc > 1) {
+    size_t len = 0;
+    uint8_t* fx = slurp(argv[1], &len);
+    CHECK(fx && len > 16 && !memcmp(fx, "G16F", 4), "fixture file loads");
+    uint32_t hdr[3];
+    memcpy(hdr, fx + 4, 12);
+    const uint32_t k = hdr[0], m = hdr[1], npub = hdr[2];
+    const size_t dn = (size_t)1 << k;
+    const uint8_t* p = fx + 16;
+    const uint8_t *a_g1 = p; p += (size_t)m * 64;
+    const uint8_t *b_g1 = p; p += (size_t)m * 64;
+    const uint8_t *b_g2 = p; p += (size_t)m * 128;
+    const uint8_t *l_g1 = p; p += (size_t)(m - npub) * 64;
+    const uint8_t *h_g1 = p; p += (dn - 1) * 64;
+    const uint8_t *wit = p; p += (size_t)m * 32;
+    uint8_t *ea = (uint8_t*)p; p += dn * 32;
+    uint8_t *eb = (uint8_t*)p; p += dn * 32;
+    uint8_t *ec = (uint8_t*)p; p += dn * 32;
+    const uint8_t* want = p; p += 256;
+    CHECK((size_t)(p - fx) == len, "fixture layout matches its header");
+    b200zk_groth16_pk pk;
+    memset(&pk, 0, sizeof pk);
+    pk.log_n = k;
+    int up = b200zk_g1_bases_upload(ctx, a_g1, m, B200ZK_POINTS_BE, &pk.handle[0]);
+    up |= b200zk_g1_bases_upload(ctx, b_g1, m, B200ZK_POINTS_BE, &pk.handle[1]);
+    up |= b200zk_g2_bases_upload(ctx, b_g2, m, B200ZK_POINTS_BE, &pk.handle[2]);
+    up |= b200zk_g1_bases_upload(ctx, l_g1, m - npub, B200ZK_POINTS_BE, &pk.handle[3]);
+    up |= b200zk_g1_bases_upload(ctx, h_g1, dn - 1, B200ZK_POINTS_BE, &pk.handle[4]);
+    for (int c = 0; c < 5 && !up; ++c) up |= b200zk_bases_precompute(ctx, pk.handle[c], 0);
+    CHECK(up == B200ZK_OK, "proving key uploaded and expanded into window tables (once per process)");
+    pk.count[0] = pk.count[1] = pk.count[2] = m; pk.count[3] = m - npub; pk.count[4] = dn - 1;
+    pk.offset[3] = npub;
+    uint8_t proof[256], b1[64];
+    rc = b200zk_groth16_commit(ctx, &pk, wit, ea, eb, ec, 0, NULL, proof, b1);
+    CHECK(rc == B200ZK_OK && !memcmp(proof, want, 256), "b200zk_groth16_commit == the proof computed in the exponent (256 bytes)");
+    rc = b200zk_groth16_commit(ctx, &pk, wit, ea, eb, ec, 0, NULL, proof, NULL);
+    CHECK(rc == B200ZK_OK && !memcmp(proof, want, 256), "second proof over the resident key: same bytes");
+    pk.count[4] = dn;  /* one more H point than the key holds */
+    rc = b200zk_groth16_commit(ctx, &pk, wit, ea, eb, ec, 0, NULL, proof, NULL);
+    CHECK(rc == B200ZK_ERR_INVALID_ARG, "a column count beyond the resident bases is rejected, not truncated");
+    for (int c = 0; c < 5; ++c) b200zk_bases_free(ctx, pk.handle[c]);
+    free(fx);
+  }
 
   free(a); free(b);
   b200zk_destroy(ctx);

@@ -33,6 +33,12 @@
  *          w = 5^((r-1)/2^28)^(2^(28-log_n)); inverse uses w^-1 and scales by n^-1; coset pre-multiplies a[j]
  *          by h^j (forward) / post-multiplies by h^-j (inverse), h = 5 unless given.
  *
+ * Threading and streams
+ *   Every entry point switches to the context's device for the duration of the call (and restores the caller's),
+ *   so a context may be used from any thread and next to contexts on other devices.  A context owns ONE set of
+ *   grow-only scratch buffers: drive it from one stream at a time (or order the streams with events yourself).
+ *   Cached tables (NTT twiddles, coset powers) carry a build event that consumers on other streams wait on.
+ *
  * There is NO CPU fallback anywhere behind this interface: without a CUDA device b200zk_init fails with
  * B200ZK_ERR_NO_DEVICE and every other call fails with B200ZK_ERR_INVALID_ARG on the NULL context.
  */
@@ -46,7 +52,7 @@
 extern "C" {
 #endif
 
-#define B200ZK_ABI_VERSION 1
+#define B200ZK_ABI_VERSION 2 /* v2: async MSM forms append a 4-byte is-infinity word; groth16 + ntt-root entry points */
 
 typedef struct b200zk_ctx b200zk_ctx;
 
@@ -72,7 +78,9 @@ enum {
   B200ZK_NTT_INVERSE = 1u << 4,
   B200ZK_NTT_COSET = 1u << 5,
   B200ZK_NTT_CANONICAL = 1u << 6,   /* NTT data are canonical little-endian limbs (converted on device) */
-  B200ZK_NTT_BE = 1u << 7           /* NTT data are 32-byte big-endian canonical values */
+  B200ZK_NTT_BE = 1u << 7,          /* NTT data are 32-byte big-endian canonical values */
+  B200ZK_G16_INPUTS_DEVICE = 1u << 8, /* b200zk_groth16_commit*: witness and evaluation buffers are DEVICE pointers (used in place) */
+  B200ZK_G16_H_COEFFS = 1u << 9     /* b200zk_groth16_commit*: a_evals already holds the quotient's coefficients (Montgomery); skip the NTTs */
 };
 
 /* ---- lifecycle (ProverBackend::new / process-global OnceLock, cf. sp1.rs:30,93-95) ------------------- */
@@ -128,13 +136,24 @@ int b200zk_g1_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_sc
                          uint32_t flags, void* stream, uint8_t out[64]);
 int b200zk_g2_msm_device(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
                          uint32_t flags, void* stream, uint8_t out[128]);
-/* fully asynchronous forms: the encoded result (BE or native per flags) is written to device memory */
+/* fully asynchronous forms: the encoded result (BE or native per flags) is written to device memory, followed by a
+ * 32-bit word that is 1 when the result is the identity (what the synchronous forms return as status 1):
+ * d_out68 = 64 + 4 bytes, d_out132 = 128 + 4 bytes */
 int b200zk_g1_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
-                               uint32_t flags, void* stream, void* d_out64);
+                               uint32_t flags, void* stream, void* d_out68);
 int b200zk_g2_msm_device_async(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n,
-                               uint32_t flags, void* stream, void* d_out128);
+                               uint32_t flags, void* stream, void* d_out132);
 int b200zk_fr_ntt_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags,
                          const uint8_t* coset_gen, void* stream);
+/* The primitive 2^28-th root of unity g of Fr that every domain generator derives from (w_n = g^(2^(28-log_n))) is a
+ * parameter of the context.  root_le = canonical little-endian 32 bytes, NULL = back to the
+ * default.  Rejected with B200ZK_ERR_INVALID_ARG unless g^(2^28) = 1 and g^(2^27) != 1.
+ *   preset 0  ark-poly 0.5.0 / gnark-crypto bn254 fr:  5^((r-1)/2^28) = 0x2a3c09f0a58a7e8500e0a7eb8ef62abc402d111e41112ed49bd61b6e725b19f0
+ *             (the SP1 / RISC0 Groth16 wraps, /root/reference/crates/prover/src/backend/sp1.rs:97-134, risc0.rs:24-29)   [default]
+ *   preset 1  halo2curves-axiom 0.7.2 bn256::Fr:       7^((r-1)/2^28) = 0x03ddb9f5166d18b798865ea93dd31f743215cf6dd39329c8d34f1ed960c37c9c
+ *             (the OpenVM halo2-KZG wrap, /root/reference/crates/prover/src/backend/openvm.rs:52-56) */
+int b200zk_set_ntt_root(b200zk_ctx* ctx, const uint8_t* root_le);
+int b200zk_ntt_root_preset(int preset, uint8_t root_le_out[32]);
 
 /* ---- multi-GPU: one process per GPU, point-split MSM ------------------------------------ */
 /* Each rank reduces its shard to ONE partial sum in extended-Jacobian XYZZ form (G1: 128 B, G2: 256 B,
@@ -207,6 +226,41 @@ int b200zk_set_profiling(b200zk_ctx* ctx, int enabled);
  * status[i] = 0, or 1 when result i is the identity.  Device scalars, like b200zk_g1_msm_resident_device. */
 int b200zk_msm_multi_resident_device(b200zk_ctx* ctx, const uint64_t* handles, size_t count, const void* d_scalars, size_t n,
                                      uint32_t flags, void* stream, uint8_t* out /* count*128 */, int* status /* count */);
+
+/* ---- the Groth16 prove arithmetic as one call --------------------------------------
+ * What the SNARK wrap behind ProofFormat::Groth16 computes after witness generation
+ * (crates/prover/src/backend/sp1.rs:97-134 -> gnark groth16.Prove; risc0.rs:24-29,71-82 -> risc0-groth16), over a
+ * proving key that lives in HBM (b200zk_g{1,2}_bases_upload + b200zk_bases_precompute, once per process -- the
+ * OnceLock setup of sp1.rs:30,93-95):
+ *     quotient  3 iNTT + 3 coset NTT + (a*b - c)/Z_H + 1 coset iNTT    (coset generator 5, the context's NTT root)
+ *     commit    [A]1, [B]1, [B]2 over the witness, [L]1 over its private part, [H]1 over the quotient's coefficients
+ *     assemble  proof = A (64) | B2 (128, x_im|x_re|y_im|y_re) | C (64), C = [L]1 + [H]1; no blinding (r = s = 0)
+ * Columns: 0 = A_g1, 1 = B_g1 (handle 0 = absent), 2 = B_g2, 3 = L_g1, 4 = H_g1.  count[k] = points of column k this
+ * context multiplies; offset[k] = index of the scalar its first point multiplies -- into the witness for columns 0..3
+ * (L_g1 of a whole key: offset = number of public inputs incl. the leading 1), into the quotient's coefficients for
+ * column 4 (count <= 2^log_n - 1 for a whole key).  A single GPU holds whole columns (offsets 0,0,0,n_public,0); a
+ * point-split rank holds a slice of each and passes the slice's start.  Columns that multiply the same scalar slice
+ * under the same window plan share ONE digit sort. */
+typedef struct b200zk_groth16_pk {
+  uint32_t log_n;      /* quotient domain 2^log_n */
+  uint32_t reserved;   /* 0 */
+  uint64_t handle[5];
+  uint64_t count[5];
+  uint64_t offset[5];
+} b200zk_groth16_pk;
+/* witness: scalars (canonical LE unless B200ZK_SCALARS_BE / _MONT), at least max(offset+count) over columns 0..3;
+ * a_evals, b_evals, c_evals: (A z), (B z), (C z) on the domain, 2^log_n Montgomery LE elements each.  HOST buffers by
+ * default (copied in, left untouched); with B200ZK_G16_INPUTS_DEVICE device pointers, used in place (a_evals is
+ * overwritten with the quotient's coefficients, b/c with their coset evaluations).  proof: 256 bytes out;
+ * b_g1 (may be NULL): [B]1 as 64 bytes.  One stream, one synchronisation at the end. */
+int b200zk_groth16_commit(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, const void* witness, void* a_evals, void* b_evals,
+                          void* c_evals, uint32_t flags, void* stream, uint8_t proof[256], uint8_t b_g1[64]);
+/* multi-GPU halves: every rank leaves its five partial sums (768 B: A | B1 | B2 | L | H, XYZZ native limbs) in device
+ * memory without synchronising; the host side all-gathers the blocks ONCE and every rank folds `count` of them */
+int b200zk_groth16_commit_partial(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, const void* witness, void* a_evals,
+                                  void* b_evals, void* c_evals, uint32_t flags, void* stream, void* d_partials768);
+int b200zk_groth16_fold(b200zk_ctx* ctx, const void* d_partials, size_t count, void* stream, uint8_t proof[256],
+                        uint8_t b_g1[64]);
 
 /* ---- batched EIP-196 / EIP-197 precompile arithmetic ------------------------------
  * The three BN254 calls of the reference's `Crypto` trait, `count` independent items per call, HOST buffers:

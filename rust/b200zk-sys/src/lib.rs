@@ -15,7 +15,7 @@ pub struct b200zk_ctx {
     _private: [u8; 0],
 }
 
-pub const B200ZK_ABI_VERSION: c_int = 1;
+pub const B200ZK_ABI_VERSION: c_int = 2;
 
 // status codes: 0..3 follow zisk.rs:144-172
 pub const B200ZK_OK: c_int = 0;
@@ -37,6 +37,19 @@ pub const B200ZK_NTT_INVERSE: u32 = 1 << 4;
 pub const B200ZK_NTT_COSET: u32 = 1 << 5;
 pub const B200ZK_NTT_CANONICAL: u32 = 1 << 6;
 pub const B200ZK_NTT_BE: u32 = 1 << 7;
+pub const B200ZK_G16_INPUTS_DEVICE: u32 = 1 << 8;
+pub const B200ZK_G16_H_COEFFS: u32 = 1 << 9;
+
+/// `struct b200zk_groth16_pk` (include/b200zk.h): columns 0..4 = A_g1, B_g1 (handle 0 = absent), B_g2, L_g1, H_g1.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b200zk_groth16_pk {
+    pub log_n: u32,
+    pub reserved: u32,
+    pub handle: [u64; 5],
+    pub count: [u64; 5],
+    pub offset: [u64; 5],
+}
 
 unsafe extern "C" {
     pub fn b200zk_abi_version() -> c_int;
@@ -65,9 +78,14 @@ unsafe extern "C" {
 
     pub fn b200zk_g1_msm_device(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, out: *mut u8) -> c_int;
     pub fn b200zk_g2_msm_device(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, out: *mut u8) -> c_int;
-    pub fn b200zk_g1_msm_device_async(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_out64: *mut c_void) -> c_int;
-    pub fn b200zk_g2_msm_device_async(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_out128: *mut c_void) -> c_int;
+    pub fn b200zk_g1_msm_device_async(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_out68: *mut c_void) -> c_int;
+    pub fn b200zk_g2_msm_device_async(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_out132: *mut c_void) -> c_int;
     pub fn b200zk_fr_ntt_device(ctx: *mut b200zk_ctx, d_data: *mut c_void, log_n: u32, flags: u32, coset_gen: *const u8, stream: *mut c_void) -> c_int;
+    pub fn b200zk_set_ntt_root(ctx: *mut b200zk_ctx, root_le: *const u8) -> c_int;
+    pub fn b200zk_ntt_root_preset(preset: c_int, root_le_out: *mut u8) -> c_int;
+    pub fn b200zk_groth16_commit(ctx: *mut b200zk_ctx, pk: *const b200zk_groth16_pk, witness: *const c_void, a_evals: *mut c_void, b_evals: *mut c_void, c_evals: *mut c_void, flags: u32, stream: *mut c_void, proof: *mut u8, b_g1: *mut u8) -> c_int;
+    pub fn b200zk_groth16_commit_partial(ctx: *mut b200zk_ctx, pk: *const b200zk_groth16_pk, witness: *const c_void, a_evals: *mut c_void, b_evals: *mut c_void, c_evals: *mut c_void, flags: u32, stream: *mut c_void, d_partials768: *mut c_void) -> c_int;
+    pub fn b200zk_groth16_fold(ctx: *mut b200zk_ctx, d_partials: *const c_void, count: usize, stream: *mut c_void, proof: *mut u8, b_g1: *mut u8) -> c_int;
 
     pub fn b200zk_g1_msm_partial_device(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial128: *mut c_void) -> c_int;
     pub fn b200zk_g2_msm_partial_device(ctx: *mut b200zk_ctx, d_points: *const c_void, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, d_partial256: *mut c_void) -> c_int;

@@ -10,6 +10,7 @@
 //! zkVM SDK and is injected through [`WrapCircuit`]; without one, `prove` returns
 //! `BackendError::NotImplemented` for `ProofFormat::Groth16`, exactly like a backend built without its SDK.
 //! Drop this file in as `crates/prover/src/backend/b200.rs` (wiring in INTEGRATION.md).
+use std::sync::OnceLock;
 use std::time::{Duration, Instant};
 
 use ethrex_common::types::prover::{ProofBytes, ProofFormat, ProverOutput, ProverType};
@@ -20,7 +21,6 @@ use tracing::info;
 use ethrex_prover::backend::{BackendError, ExecBackend, ProverBackend};
 
 use crate::ffi;
-use b200zk_sys::{B200ZK_NTT_COSET, B200ZK_NTT_INVERSE};
 
 /// What the zkVM SDK has to provide for the Groth16 wrap: the witness vector and the proving-key columns.
 /// All buffers use the library's native formats (ark-ff Montgomery limbs for points, canonical limbs for
@@ -30,20 +30,23 @@ pub trait WrapCircuit: Send + Sync {
     fn prover_type(&self) -> ProverType;
     /// log2 of the evaluation-domain size.
     fn domain_log2(&self) -> u32;
-    /// Full witness assignment (public inputs first), canonical 32-byte little-endian scalars.
+    /// Number of public R1CS variables INCLUDING the leading constant 1: the L column starts behind them.
+    fn n_public(&self) -> usize;
+    /// Full witness assignment (1, public inputs, private variables), canonical 32-byte little-endian scalars --
+    /// one scalar per point of `pk_a_g1`.
     fn witness(&self, serialized_input: &[u8]) -> Result<Vec<u8>, BackendError>;
-    /// Proving-key columns as native affine points: A (G1), B (G1), B (G2), K/L (G1), H (G1).
+    /// Proving-key columns as native affine points: A (G1), B (G1), B (G2) with one point per variable; L (G1) with
+    /// one point per PRIVATE variable; H (G1) with one point per quotient coefficient (2^k - 1 points).
     fn pk_a_g1(&self) -> &[u8];
     fn pk_b_g1(&self) -> &[u8];
     fn pk_b_g2(&self) -> &[u8];
     fn pk_l_g1(&self) -> &[u8];
     fn pk_h_g1(&self) -> &[u8];
-    /// Evaluations of A*w, B*w, C*w over the domain (Montgomery limbs), from which the quotient H is built.
+    /// Evaluations of A*w, B*w, C*w over the domain (Montgomery limbs), from which the library builds the quotient H.
     fn abc_evaluations(&self, witness: &[u8]) -> Result<[Vec<u8>; 3], BackendError>;
-    /// (a .* b - c) ./ Z_H on the coset, element-wise, done by the SDK's field code.
-    fn quotient_on_coset(&self, abc_coset: &mut [Vec<u8>; 3]) -> Result<Vec<u8>, BackendError>;
-    /// Assemble (A, B, C) with the blinding terms and the verifier's byte order.
-    fn assemble(&self, commitments: &Groth16Commitments) -> Result<Vec<u8>, BackendError>;
+    /// Final assembly with the SDK's blinding terms and selector bytes (`sp1.rs:176-194`, `risc0.rs:43-59`); `proof`
+    /// is the unblinded A | B2 | C the device produced, `b_g1` the [B]1 commitment blinding needs.
+    fn assemble(&self, proof: &[u8; 256], b_g1: &[u8; 64]) -> Result<Vec<u8>, BackendError>;
     /// The ecpairing calldata of the Groth16 verification equation for `proof`
     /// (`-A | B | alpha | beta | IC(public inputs) | gamma | C | delta`, 4 x 192 bytes), when the SDK exposes its
     /// verifying key; `None` makes `verify` answer "not implemented", like the reference's default.
@@ -52,54 +55,80 @@ pub trait WrapCircuit: Send + Sync {
     }
 }
 
-/// The five commitments of a Groth16 proof before blinding, EIP-196/197 encoded.
-pub struct Groth16Commitments {
-    pub a_g1: [u8; 64],
-    pub b_g1: [u8; 64],
-    pub b_g2: [u8; 128],
-    pub l_g1: [u8; 64],
-    pub h_g1: [u8; 64],
-}
-
 pub struct B200ProveOutput {
     pub prover_type: ProverType,
     pub proof: Vec<u8>,
 }
 
+/// The proving key as it lives in HBM across proofs: uploaded and expanded into window tables ONCE per process, like
+/// `static PROVER_SETUP: OnceLock<ProverSetup>` in the reference (`sp1.rs:30,93-95`).
+struct ResidentKey {
+    pk: b200zk_sys::b200zk_groth16_pk,
+}
+
 #[derive(Default)]
 pub struct B200Backend {
     circuit: Option<Box<dyn WrapCircuit>>,
+    resident: OnceLock<Result<ResidentKey, String>>,
+}
+
+fn count_of(bytes: &[u8], point: usize) -> Result<u64, BackendError> {
+    if bytes.len() % point != 0 {
+        return Err(BackendError::serialization("proving-key column is not a whole number of points"));
+    }
+    u64::try_from(bytes.len() / point).map_err(BackendError::serialization)
 }
 
 impl B200Backend {
     pub fn new() -> Self {
-        Self { circuit: None }
+        Self { circuit: None, resident: OnceLock::new() }
     }
 
     pub fn with_circuit(circuit: Box<dyn WrapCircuit>) -> Self {
-        Self { circuit: Some(circuit) }
+        Self { circuit: Some(circuit), resident: OnceLock::new() }
     }
 
-    /// The hot path: 3 iNTT + 3 coset NTT + 1 coset iNTT, then 4 G1 MSMs and 1 G2 MSM on the GPU.
-    fn commit(circuit: &dyn WrapCircuit, serialized: &[u8]) -> Result<Groth16Commitments, BackendError> {
+    /// Upload + precompute the five columns once; checks the column sizes against each other instead of truncating.
+    fn load_key(circuit: &dyn WrapCircuit, gpu: &mut ffi::B200zk) -> Result<ResidentKey, BackendError> {
+        let k = circuit.domain_log2();
+        let n = 1u64.checked_shl(k).ok_or_else(|| BackendError::serialization("domain too large"))?;
+        let n_pub = u64::try_from(circuit.n_public()).map_err(BackendError::serialization)?;
+        let m = count_of(circuit.pk_a_g1(), 64)?;
+        let (mb1, mb2) = (count_of(circuit.pk_b_g1(), 64)?, count_of(circuit.pk_b_g2(), 128)?);
+        let (ml, mh) = (count_of(circuit.pk_l_g1(), 64)?, count_of(circuit.pk_h_g1(), 64)?);
+        if mb1 != m || mb2 != m || n_pub > m || ml != m.saturating_sub(n_pub) || mh.saturating_add(1) != n {
+            return Err(BackendError::serialization(format!(
+                "proving-key columns disagree: A {m}, B1 {mb1}, B2 {mb2} (must be equal), L {ml} (must be A - {n_pub} public), H {mh} (must be 2^{k} - 1)"
+            )));
+        }
+        let handles = [
+            gpu.g1_bases_upload(circuit.pk_a_g1(), 0)?,
+            gpu.g1_bases_upload(circuit.pk_b_g1(), 0)?,
+            gpu.g2_bases_upload(circuit.pk_b_g2(), 0)?,
+            gpu.g1_bases_upload(circuit.pk_l_g1(), 0)?,
+            gpu.g1_bases_upload(circuit.pk_h_g1(), 0)?,
+        ];
+        for h in handles {
+            gpu.bases_precompute(h, 0)?;
+        }
+        Ok(ResidentKey {
+            pk: b200zk_sys::b200zk_groth16_pk { log_n: k, reserved: 0, handle: handles, count: [m, m, m, ml, mh], offset: [0, 0, 0, n_pub, 0] },
+        })
+    }
+
+    /// The hot path: one call -- 3 iNTT + 3 coset NTT + quotient + 1 coset iNTT, 4 G1 MSMs + 1 G2 MSM over the
+    /// resident key (A, B1, B2 share one digit sort), C = L + H -- and one synchronisation.
+    fn commit(&self, circuit: &dyn WrapCircuit, serialized: &[u8]) -> Result<([u8; 256], [u8; 64]), BackendError> {
         let gpu = ffi::global()?;
         let mut gpu = gpu.lock().map_err(|_| BackendError::proving("b200zk context poisoned"))?;
-        let k = circuit.domain_log2();
+        let key = self
+            .resident
+            .get_or_init(|| Self::load_key(circuit, &mut gpu).map_err(|e| e.to_string()))
+            .as_ref()
+            .map_err(BackendError::proving)?;
         let witness = circuit.witness(serialized)?;
-        let mut abc = circuit.abc_evaluations(&witness)?;
-        for poly in abc.iter_mut() {
-            gpu.fr_ntt(poly, k, B200ZK_NTT_INVERSE, None)?; // evaluations -> coefficients
-            gpu.fr_ntt(poly, k, B200ZK_NTT_COSET, None)?; // coefficients -> coset evaluations
-        }
-        let mut h = circuit.quotient_on_coset(&mut abc)?;
-        gpu.fr_ntt(&mut h, k, B200ZK_NTT_INVERSE | B200ZK_NTT_COSET, None)?;
-        Ok(Groth16Commitments {
-            a_g1: gpu.g1_msm(circuit.pk_a_g1(), &witness, 0)?,
-            b_g1: gpu.g1_msm(circuit.pk_b_g1(), &witness, 0)?,
-            b_g2: gpu.g2_msm(circuit.pk_b_g2(), &witness, 0)?,
-            l_g1: gpu.g1_msm(circuit.pk_l_g1(), &witness, 0)?,
-            h_g1: gpu.g1_msm(circuit.pk_h_g1(), &h, b200zk_sys::B200ZK_SCALARS_MONT)?,
-        })
+        let [mut a, mut b, mut c] = circuit.abc_evaluations(&witness)?;
+        gpu.groth16_commit(&key.pk, &witness, &mut a, &mut b, &mut c)
     }
 }
 
@@ -127,8 +156,8 @@ impl ProverBackend for B200Backend {
         ExecBackend::new().execute(input)?;
         match (format, self.circuit.as_deref()) {
             (ProofFormat::Groth16, Some(circuit)) => {
-                let commitments = Self::commit(circuit, &serialized)?;
-                Ok(B200ProveOutput { prover_type: circuit.prover_type(), proof: circuit.assemble(&commitments)? })
+                let (proof, b_g1) = self.commit(circuit, &serialized)?;
+                Ok(B200ProveOutput { prover_type: circuit.prover_type(), proof: circuit.assemble(&proof, &b_g1)? })
             }
             (ProofFormat::Groth16, None) => Err(BackendError::not_implemented(
                 "b200 backend built without a wrap circuit: ProofFormat::Groth16 needs a zkVM SDK's proving key",
@@ -163,7 +192,9 @@ impl ProverBackend for B200Backend {
         let start = Instant::now();
         let proof = self.prove(input, format)?;
         let elapsed = start.elapsed();
-        info!("b200 backend proved in {:.2?}", elapsed);
+        // the caller (`Prover::poll_endpoints`, crates/prover/src/prover.rs:106-118) logs `proving_time_s` / `proving_time_ms`
+        // from this Duration; the backend adds the same two fields for its own share of it
+        info!(proving_time_s = elapsed.as_secs(), proving_time_ms = u64::try_from(elapsed.as_millis()).unwrap_or(u64::MAX), "b200 backend proved in {:.2?}", elapsed);
         Ok((proof, elapsed))
     }
 }

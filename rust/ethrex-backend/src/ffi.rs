@@ -116,6 +116,66 @@ impl B200zk {
         Ok(handle)
     }
 
+    pub fn g2_bases_upload(&mut self, points: &[u8], flags: u32) -> Result<u64, BackendError> {
+        let mut handle = 0u64;
+        // SAFETY: slice is valid for points.len() bytes.
+        let status = unsafe { sys::b200zk_g2_bases_upload(self.ctx.as_ptr(), points.as_ptr().cast(), points.len() / 128, flags, &mut handle) };
+        check(self, status)?;
+        Ok(handle)
+    }
+
+    /// One-off per proving-key column: expand the resident bases into their window multiples (`window_bits` 0 = automatic).
+    pub fn bases_precompute(&mut self, handle: u64, window_bits: u32) -> Result<(), BackendError> {
+        // SAFETY: plain value arguments.
+        let status = unsafe { sys::b200zk_bases_precompute(self.ctx.as_ptr(), handle, window_bits) };
+        check(self, status).map(|_| ())
+    }
+
+    pub fn bases_free(&mut self, handle: u64) -> Result<(), BackendError> {
+        // SAFETY: plain value arguments.
+        let status = unsafe { sys::b200zk_bases_free(self.ctx.as_ptr(), handle) };
+        check(self, status).map(|_| ())
+    }
+
+    /// Selects the 2^28-th root of unity the NTT domains derive from (`None` = ark/gnark default; halo2curves'
+    /// value comes from `b200zk_ntt_root_preset(1, ..)`), for wraps built on another FFT convention (`openvm.rs:52-56`).
+    pub fn set_ntt_root(&mut self, root_le: Option<&[u8; 32]>) -> Result<(), BackendError> {
+        let p = root_le.map_or(std::ptr::null(), |g| g.as_ptr());
+        // SAFETY: NULL or 32 valid bytes.
+        let status = unsafe { sys::b200zk_set_ntt_root(self.ctx.as_ptr(), p) };
+        check(self, status).map(|_| ())
+    }
+
+    /// The whole Groth16 prove arithmetic (quotient NTTs, five MSMs over the RESIDENT proving key, C = L + H) in one
+    /// call with one synchronisation.  `witness`: canonical LE scalars; `a`, `b`, `c`: (A z), (B z), (C z) on the
+    /// domain, Montgomery LE, 2^log_n elements each.  Returns (A | B2 | C, [B]1).
+    pub fn groth16_commit(&mut self, pk: &sys::b200zk_groth16_pk, witness: &[u8], a: &mut [u8], b: &mut [u8], c: &mut [u8]) -> Result<([u8; 256], [u8; 64]), BackendError> {
+        let n_bytes = 32usize.checked_shl(pk.log_n).ok_or_else(|| BackendError::serialization("groth16_commit: log_n too large"))?;
+        if a.len() != n_bytes || b.len() != n_bytes || c.len() != n_bytes {
+            return Err(BackendError::serialization("groth16_commit: evaluation vectors must hold 2^log_n elements"));
+        }
+        // the witness must reach the end of every column that multiplies it (columns 0..3)
+        let mut wit_end = 0u64;
+        for ((h, cnt), off) in pk.handle.iter().zip(pk.count.iter()).zip(pk.offset.iter()).take(4) {
+            if *h != 0 {
+                wit_end = wit_end.max(off.checked_add(*cnt).ok_or_else(|| BackendError::serialization("groth16_commit: column range overflows"))?);
+            }
+        }
+        let have = u64::try_from(witness.len() / 32).map_err(BackendError::serialization)?;
+        if have < wit_end {
+            return Err(BackendError::serialization(format!("groth16_commit: witness holds {have} scalars, the proving key multiplies {wit_end}")));
+        }
+        let mut proof = [0u8; 256];
+        let mut b1 = [0u8; 64];
+        // SAFETY: lengths checked above; host buffers outlive the synchronous call; NULL stream = the context's own.
+        let status = unsafe {
+            sys::b200zk_groth16_commit(self.ctx.as_ptr(), pk, witness.as_ptr().cast(), a.as_mut_ptr().cast(), b.as_mut_ptr().cast(), c.as_mut_ptr().cast(), 0,
+                                       std::ptr::null_mut(), proof.as_mut_ptr(), b1.as_mut_ptr())
+        };
+        check(self, status)?;
+        Ok((proof, b1))
+    }
+
     pub fn g1_msm_resident(&mut self, handle: u64, scalars: &[u8], flags: u32) -> Result<[u8; 64], BackendError> {
         let mut out = [0u8; 64];
         // SAFETY: slice valid; n derived from its length.

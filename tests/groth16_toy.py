@@ -106,3 +106,21 @@ class ToyGroth16:
         neg_a = A[:32] + ((o.P - ay) % o.P).to_bytes(32, "big") if (ax or ay) else A
         ic = _g1(self.ic[0] + self.ic[1] * (public_x % R))
         return neg_a + B + self.vk_alpha_g1 + self.vk_beta_g2 + ic + self.vk_gamma_g2 + C + self.vk_delta_g2
+
+
+def write_c_fixture(path: str, log_n: int = 4, public_x: int = 0x1234567):
+    """Binary fixture for examples/c_abi_demo.c section 6 (little-endian host):
+    "G16F" | u32 log_n | u32 m | u32 n_public | A_g1 (m x 64, EIP-196) | B_g1 (m x 64) | B_g2 (m x 128, EIP-197) |
+    L_g1 ((m - n_public) x 64) | H_g1 ((2^log_n - 1) x 64) | witness (m x 32, canonical LE) |
+    (A z), (B z), (C z) on the domain (2^log_n x 32 each, Montgomery LE) | expected proof (256)."""
+    import struct
+    toy = ToyGroth16(log_n)
+    z = toy.assign(public_x)
+    a, b, c = toy.evaluations(z)
+    r_mont = (1 << 256) % R
+    le = lambda vals, mont: b"".join(int(v % R * (r_mont if mont else 1) % R).to_bytes(32, "little") for v in vals)  # noqa: E731
+    blob = b"G16F" + struct.pack("<III", log_n, toy.m, N_PUBLIC) + toy.a_g1 + toy.b_g1 + toy.b_g2 + toy.l_g1 + toy.h_g1
+    blob += le(z, False) + le(a, True) + le(b, True) + le(c, True) + toy.expected_proof(z)
+    with open(path, "wb") as f:
+        f.write(blob)
+    return toy

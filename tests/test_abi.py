@@ -34,7 +34,7 @@ def test_rust_sys_crate_declares_the_same_symbols():
 
 def test_status_strings_and_version():
     from ethrex_b200 import _ffi
-    assert _ffi.lib.b200zk_abi_version() == 1
+    assert _ffi.lib.b200zk_abi_version() == 2
     assert b"no CPU fallback" in _ffi.lib.b200zk_strerror(_ffi.ERR_NO_DEVICE)
     assert _ffi.lib.b200zk_strerror(_ffi.ERR_NOT_ON_CURVE) == b"input point not on curve"
     # null-context calls are rejected, not crashed

@@ -68,10 +68,15 @@ def test_groth16_pipeline_matches_oracle(ctx):
                 exp[name] = orc.g2_msm(orc.g2_chain(n, k, d)[:cnt], sc[:cnt])
             else:
                 exp[name] = orc.g1_msm(orc.g1_chain(n, k, d)[:cnt], sc[:cnt])
-        for name in exp:
-            assert proof.commitments[name] == exp[name], name
         c_pt = orc.g1_add_be(exp["l_g1"], exp["h_g1"])[1]
+        # the one-call path (b200zk_groth16_commit) reports A, B1, B2 and C = L + H
+        assert proof.commitments == {"a_g1": exp["a_g1"], "b_g1": exp["b_g1"], "b_g2": exp["b_g2"], "c_g1": c_pt}
         assert proof.proof == exp["a_g1"] + exp["b_g2"] + c_pt
+        # the separate-call path (five read-back MSMs) reports every commitment and lands on the same proof
+        proof2, cm = circuit.prove_separate(ser)
+        for name in exp:
+            assert cm[name] == exp[name], name
+        assert proof2 == proof.proof
         # deterministic: same input, same proof; different input, different proof
         assert backend.prove(inp).proof == proof.proof
         assert backend.prove({"blocks": [9]}).proof != proof.proof
@@ -101,6 +106,14 @@ def test_groth16_verifier_host_logic_without_a_gpu():
         assert ver.calldata(proof, [x]) == toy.verifier_calldata(proof, x)
     with pytest.raises(ValueError):
         ver.calldata(proof[:255], [1])
+    # non-canonical encodings are rejected, never reduced: A = (x, y + p), public input x + r, negative input
+    x = 12345
+    proof = toy.expected_proof(toy.assign(x))
+    ay = int.from_bytes(proof[32:64], "big")
+    assert ver.calldata(proof[:32] + (ay + pyref.P).to_bytes(32, "big") + proof[64:], [x]) is None
+    assert ver.calldata((pyref.P).to_bytes(32, "big") + proof[32:], [x]) is None
+    assert ver.calldata(proof, [x + pyref.R]) is None and ver.calldata(proof, [-1]) is None
+    assert ver.calldata(proof, [x]) is not None
 
     class Stub:
         def __init__(self, answer): self.answer = answer
@@ -114,3 +127,20 @@ def test_groth16_verifier_host_logic_without_a_gpu():
     with pytest.raises(eb.B200Error) as e:
         B200Backend(None).verify(out, [1])
     assert e.value.kind == "NotImplemented"
+
+
+def test_timed_log_line_has_the_reference_fields():
+    """`--timed` log line of /root/reference/crates/prover/src/prover.rs:106-118: id, proving_time_s, proving_time_ms."""
+    from ethrex_b200.backend import log_proved
+    line = log_proved(7, 1.2345)
+    assert "id=7" in line and "proving_time_s=1 " in line and "proving_time_ms=1234 " in line and "Proved payload #7 in 1.23s" in line
+
+
+def test_host_buffer_length_guard():
+    from ethrex_b200.context import _need
+    _need(bytes(64), 64, "x")
+    _need(np.zeros(8, dtype=np.uint64), 64, "x")
+    with pytest.raises(eb.B200Error, match="holds 63 bytes, the call needs 64"):
+        _need(bytes(63), 64, "x")
+    with pytest.raises(eb.B200Error):
+        _need(np.zeros(7, dtype=np.uint64), 64, "x")

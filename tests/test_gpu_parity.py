@@ -727,6 +727,22 @@ def test_c_abi_from_plain_c():
 
 
 @pytest.mark.gpu
+def test_groth16_commit_from_plain_c(tmp_path):
+    """b200zk_groth16_commit driven from C only (examples/c_abi_demo.c section 6): a real Groth16 instance (trusted
+    setup with known toxic waste, tests/groth16_toy.py) uploaded once, proved in ONE call, bit-exact against the proof
+    computed in the exponent -- the orchestration a Rust / cgo caller gets without re-implementing it."""
+    import subprocess
+    from groth16_toy import write_c_fixture
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "build", "c_abi_demo")
+    assert os.path.exists(exe), "build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+    fx = str(tmp_path / "groth16_toy_2_4.bin")
+    write_c_fixture(fx, log_n=4)
+    r = subprocess.run([exe, fx], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "b200zk_groth16_commit == the proof computed in the exponent" in r.stdout and "all checks passed" in r.stdout
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("precompute", [False, True])
 def test_multi_msm_shares_one_sort_and_matches_single_calls(ctx, precompute):
     """b200zk_msm_multi_resident_device (Groth16's witness MSMs): G1, G1, G2, G1 columns against one scalar vector

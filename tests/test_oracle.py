@@ -240,3 +240,25 @@ def test_groth16_golden_fixture_is_current():
         proof = toy.expected_proof(toy.assign(x))
         assert proof.hex() == case["proof"] and toy.verifier_calldata(proof, x).hex() == case["verifier_calldata"]
     assert tw.pairing_check(_pairs(bytes.fromhex(inst["cases"][0]["verifier_calldata"])))
+
+
+def test_ntt_root_presets_in_the_library_are_the_published_generators():
+    """b200zk_ntt_root_preset (no device needed): preset 0 = ark-poly / gnark-crypto 5^((r-1)/2^28), preset 1 =
+    halo2curves 7^((r-1)/2^28) -- the value SURVEY.md section 8c records -- and the oracle's NTT accepts either."""
+    import ctypes
+    from ethrex_b200 import _ffi
+    buf = ctypes.create_string_buffer(32)
+    assert _ffi.lib.b200zk_ntt_root_preset(0, buf) == 0 and int.from_bytes(buf.raw, "little") == o.ROOT_2_28 == pow(5, (o.R - 1) >> 28, o.R)
+    halo2 = pow(7, (o.R - 1) >> 28, o.R)
+    assert _ffi.lib.b200zk_ntt_root_preset(1, buf) == 0 and int.from_bytes(buf.raw, "little") == halo2
+    assert halo2 == 0x03ddb9f5166d18b798865ea93dd31f743215cf6dd39329c8d34f1ed960c37c9c
+    assert pow(halo2, 1 << 28, o.R) == 1 and pow(halo2, 1 << 27, o.R) == o.R - 1
+    assert _ffi.lib.b200zk_ntt_root_preset(2, buf) == _ffi.ERR_INVALID_ARG
+    # the C++ oracle under halo2's root = the definition sum_j a_j w^(jk) with w = halo2^(2^(28-k))
+    import cpu_oracle as orc
+    n, log_n = 8, 3
+    a = [3, 1, 4, 1, 5, 9, 2, 6]
+    w = pow(halo2, 1 << (28 - log_n), o.R)
+    want = [sum(a[j] * pow(w, j * k, o.R) for j in range(n)) % o.R for k in range(n)]
+    got = orc.array_to_ints(orc.fr_from_mont(orc.fr_ntt(orc.fr_to_mont(orc.ints_to_array(a)), log_n, 0, root_2_28=halo2)))
+    assert got == want
