@@ -1,6 +1,7 @@
 // common.cuh -- context, workspace and launch bookkeeping shared by the translation units of libb200zk.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in nsys / ncu --nvtx timelines, no-ops otherwise
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -26,7 +27,7 @@ struct TwiddleSet {   // per (log_n, direction): see ntt.cu
 };
 
 struct SortSlot {  // one of the two sort workspaces of the chunk-pipelined MSM
-  DevBuf hist, offsets, cursor, run_off, tsum, digits, idx;
+  DevBuf hist, offsets, cursor, run_off, tsum, digits, idx, key, ctab;
   cudaEvent_t sorted = nullptr, released = nullptr;
 };
 
@@ -51,9 +52,12 @@ struct b200zk_ctx {
   cudaEvent_t ev_in = nullptr;
   b200zk::SortSlot slot[2];
   b200zk::DevBuf ws_totals, ws_bitpart;
+  b200zk::DevBuf ws_key, ws_ctab;  // two-level sort: 16-bit fine keys of the coarse-partitioned entries; per-(bin, CTA) counts / bases
   b200zk::DevBuf ws_g16[4];   // b200zk_groth16_commit: staged A/B/C evaluations (host inputs) and the 768-byte partial block
   b200zk::DevBuf ws_zinv;     // 1/(5^n - 1) of the last quotient domain, canonical limbs (cached per log_n)
   uint32_t zinv_log_n = 0xffffffffu;
+  // cudaFuncSetAttribute (opt-in to > 48 KiB dynamic shared memory) is per DEVICE: remembered per context, not per process
+  bool attr_sort = false, attr_acc = false, attr_ntt512 = false, attr_ntt256 = false;
   int msm_pair_rounds = -1;  // batched-affine pair-summing rounds before the XYZZ accumulation; <0 = automatic
   bool profiling = false;
   float phase_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -119,6 +123,15 @@ struct DeviceGuard {
   ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
   DeviceGuard(const DeviceGuard&) = delete;
   DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// NVTX range over one library phase (the reference's tracing spans around proving, e.g.
+// crates/prover/src/prover.rs:106-118; here per C-ABI call and per MSM / NTT phase)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 inline cudaStream_t pick_stream(b200zk_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }

@@ -25,6 +25,7 @@ static int stage(b200zk_ctx* ctx, DevBuf& buf, const void* host, size_t bytes, c
 
 int groth16_commit_partials(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, const void* witness, void* a_evals, void* b_evals, void* c_evals,
                             uint32_t flags, cudaStream_t st, void* d_partials) {
+  NvtxRange nvtx_g16("b200zk:groth16_commit");
   if (!pk || !d_partials) return fail(ctx, B200ZK_ERR_INVALID_ARG, "groth16_commit: null argument");
   if (pk->log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "groth16_commit: log_n > 28");
   const size_t n = (size_t)1 << pk->log_n;
@@ -53,6 +54,7 @@ int groth16_commit_partials(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, const 
   }
   // ---- quotient: H(x) = (A(x) B(x) - C(x)) / Z_H(x), coefficients left in d_a (Montgomery)
   if (!h_ready) {
+    NvtxRange nvtx_q("b200zk:groth16_quotient");
     void* polys[3] = {d_a, d_b, d_c};
     for (void* p : polys) {
       B2_TRY(ntt_run(ctx, p, pk->log_n, B200ZK_NTT_INVERSE, nullptr, st));

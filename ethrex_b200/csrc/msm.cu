@@ -232,6 +232,225 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
   }
 }
 
+// ---- two-level sort (r2): tile-local counting sort in shared memory, no per-entry global atomic ------------------------
+// The r1 sort paid, per entry, one divergent L2 reduction (msm_hist), one divergent L2 atomic WITH return and one
+// divergent 4-byte store (msm_scatter): the SM's address-divergence unit was the limit (profiles/r1f_prof_sort_summary.md).
+// Here the (window,bucket) key g of an entry is split into a coarse bin (g >> fb) and a fine key (g & (2^fb - 1)):
+//   msm_sort_count   every CTA owns a CONTIGUOUS range of scalars; it recodes them (scalar tiles staged by the copy engine,
+//                    as in msm_hist) and counts its entries per coarse bin in shared memory -> cnt[bin][cta]
+//   (scan)           exclusive scan of cnt in (bin, cta) order: every (bin, cta) pair owns a private, contiguous output run
+//   msm_sort_coarse  the same CTA walks the same scalars in tiles of 1024; a tile's entries are ranked per bin with
+//                    shared-memory atomics, permuted in shared memory, and copied out so that adjacent lanes write adjacent
+//                    addresses (value u32 + fine key u16) -- no global atomics, runs instead of scattered stores
+//   msm_sort_fine    one CTA per coarse bin: fine histogram in shared memory (-> the bucket offsets and counts the
+//                    accumulation needs, for free), then the final placement with shared-memory cursors; the bin's output
+//                    region is a few MB, so its 4-byte stores combine in L2
+// Order inside a bucket is not deterministic (shared-memory atomics); the sum is.
+static constexpr uint32_t kSortTile = 1024;        // scalars per coarse tile = threads of msm_sort_coarse
+static constexpr uint32_t kSortMaxW = 16;          // windows per scalar the staging buffers are sized for (c >= 16)
+static constexpr uint32_t kSortMaxBins = 1024;     // coarse bins
+static constexpr uint32_t kSortMaxFine = 2048;     // fine keys per bin
+static constexpr uint32_t kSortCountSub = 4;       // msm_sort_count CTAs per coarse CTA range
+
+struct SortPlan {
+  uint32_t fb;        // fine bits
+  uint32_t C;         // coarse bins = ceil(G / 2^fb)
+  uint32_t NC;        // coarse CTAs (ranges of scalars)
+  uint32_t range;     // scalars per range (multiple of kSortTile)
+  uint32_t G;
+};
+static bool make_sort_plan(size_t n, const MsmPlan& pl, int sm_count, SortPlan* sp) {
+  const size_t G = (size_t)pl.Wr * pl.B;
+  uint32_t kb = 0;
+  while (((size_t)1 << kb) < G) ++kb;
+  if (pl.W > kSortMaxW || kb < 12 || n < ((size_t)1 << 16)) return false;
+  uint32_t cb = kb > 19 ? 10 : 9;
+  if (kb - cb > 11) return false;  // would need more than kSortMaxFine keys per bin
+  sp->fb = kb - cb;
+  sp->C = (uint32_t)((G + ((size_t)1 << sp->fb) - 1) >> sp->fb);
+  sp->G = (uint32_t)G;
+  uint32_t nc = (uint32_t)sm_count;
+  size_t tiles = (n + kSortTile - 1) / kSortTile;
+  if (nc > tiles) nc = (uint32_t)tiles;
+  size_t per = ((tiles + nc - 1) / nc) * kSortTile;
+  sp->NC = (uint32_t)((n + per - 1) / per);
+  sp->range = (uint32_t)per;
+  return true;
+}
+
+// digit codes of one scalar: code[w] = bucket | sign << 31, or kNoDigit
+// (fully unrolled over kSortMaxW with a guard, so that `code` stays in registers)
+B2_D void recode_scalar(const uint32_t s[8], const MsmPlan& pl, uint32_t (&code)[kSortMaxW]) {
+  uint32_t carry = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < kSortMaxW; ++w) {
+    code[w] = kNoDigit;
+    if (w < pl.W) {
+      uint32_t coef = window_bits(s, w, pl.c) + carry;
+      carry = 0;
+      uint32_t neg = 0, mag = coef;
+      if (w + 1 < pl.W && coef >= pl.B) { carry = 1; neg = 0x80000000u; mag = (1u << pl.c) - coef; }  // ark make_digits rule
+      code[w] = mag ? ((mag - 1) | neg) : kNoDigit;
+    }
+  }
+}
+
+// grid = NC * kSortCountSub; CTA (r, sub) counts quarter `sub` of range r.  cnt[bin * NC + r] accumulates (zeroed before).
+__global__ void __launch_bounds__(kHistTile) msm_sort_count(const void* scalars, size_t n, uint32_t flags, MsmPlan pl, SortPlan sp, uint32_t* cnt) {
+  __shared__ __align__(128) uint4 tile[2][kHistTile * 2];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t sh[kSortMaxBins];
+  const uint32_t r = blockIdx.x / kSortCountSub, sub = blockIdx.x % kSortCountSub;
+  for (uint32_t b = threadIdx.x; b < sp.C; b += kHistTile) sh[b] = 0;
+  const size_t lo = (size_t)r * sp.range, hi = lo + sp.range < n ? lo + sp.range : n;
+  const size_t tiles_all = lo < hi ? (hi - lo + kHistTile - 1) / kHistTile : 0;
+  const size_t per = (tiles_all + kSortCountSub - 1) / kSortCountSub;
+  const size_t t0 = sub * per, t1 = t0 + per < tiles_all ? t0 + per : tiles_all;
+  if (threadIdx.x == 0) { tma::barrier_init(&bar[0], 1); tma::barrier_init(&bar[1], 1); tma::barrier_init_fence(); }
+  __syncthreads();
+  auto issue = [&](size_t tl, uint32_t buf) {
+    size_t first = lo + tl * kHistTile;
+    uint32_t bytes = (uint32_t)((hi - first < kHistTile ? hi - first : kHistTile) * 32);
+    tma::barrier_expect(&bar[buf], bytes);
+    tma::bulk_load(tile[buf], reinterpret_cast<const uint8_t*>(scalars) + first * 32, bytes, &bar[buf]);
+  };
+  if (threadIdx.x == 0 && t0 < t1) issue(t0, 0);
+  uint32_t it = 0;
+  for (size_t tl = t0; tl < t1; ++tl, ++it) {
+    const uint32_t buf = it & 1;
+    if (threadIdx.x == 0 && tl + 1 < t1) issue(tl + 1, buf ^ 1);
+    tma::barrier_wait(&bar[buf], (it >> 1) & 1);
+    const size_t i = lo + tl * kHistTile + threadIdx.x;
+    if (i < hi) {
+      uint32_t s[8], code[kSortMaxW];
+      decode_scalar(tile[buf][2 * threadIdx.x], tile[buf][2 * threadIdx.x + 1], flags, s);
+      recode_scalar(s, pl, code);
+#pragma unroll
+      for (uint32_t w = 0; w < kSortMaxW; ++w)
+        if (code[w] != kNoDigit) {
+          const uint32_t g = (pl.merged ? 0u : w * pl.B) + (code[w] & 0x7fffffffu);
+          atomicAdd(&sh[g >> sp.fb], 1u);
+        }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < sp.C; b += kHistTile) if (sh[b]) atomicAdd(&cnt[(size_t)b * sp.NC + r], sh[b]);
+}
+
+// grid = NC, block = kSortTile.  base[bin * NC + r] = first output slot of (bin, range r).
+struct SortCoarseSmem {
+  uint32_t val[kSortTile * kSortMaxW];
+  uint16_t key[kSortTile * kSortMaxW];
+  uint16_t bin[kSortTile * kSortMaxW];
+  uint32_t run_base[kSortMaxBins], tile_cnt[kSortMaxBins], tile_start[kSortMaxBins];
+  uint32_t warp_tot[kSortTile / 32];
+  uint32_t total;
+};
+__global__ void __launch_bounds__(kSortTile, 1) msm_sort_coarse(const void* __restrict__ scalars, size_t n, uint32_t flags, MsmPlan pl, SortPlan sp, const uint32_t* __restrict__ base,
+                                                               uint32_t* __restrict__ val1, uint16_t* __restrict__ key1) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SortCoarseSmem& sm = *reinterpret_cast<SortCoarseSmem*>(smem_raw);
+  const uint32_t r = blockIdx.x, tid = threadIdx.x;
+  const size_t lo = (size_t)r * sp.range, hi = lo + sp.range < n ? lo + sp.range : n;
+  const uint32_t fmask = (1u << sp.fb) - 1u;
+  for (uint32_t b = tid; b < sp.C; b += kSortTile) { sm.run_base[b] = __ldg(base + (size_t)b * sp.NC + r); sm.tile_cnt[b] = 0; }
+  __syncthreads();
+  const uint4* sc = reinterpret_cast<const uint4*>(scalars);
+  for (size_t t0 = lo; t0 < hi; t0 += kSortTile) {
+    const size_t i = t0 + tid;
+    uint32_t code[kSortMaxW], rank[kSortMaxW];
+    const bool live = i < hi;
+#pragma unroll
+    for (uint32_t w = 0; w < kSortMaxW; ++w) { code[w] = kNoDigit; rank[w] = 0; }
+    if (live) {
+      uint32_t s[8];
+      decode_scalar(__ldg(sc + 2 * i), __ldg(sc + 2 * i + 1), flags, s);
+      recode_scalar(s, pl, code);
+#pragma unroll
+      for (uint32_t w = 0; w < kSortMaxW; ++w)
+        if (code[w] != kNoDigit) {
+          const uint32_t g = (pl.merged ? 0u : w * pl.B) + (code[w] & 0x7fffffffu);
+          rank[w] = atomicAdd(&sm.tile_cnt[g >> sp.fb], 1u);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of tile_cnt over the C <= 1024 bins: one bin per thread
+    {
+      const uint32_t v = tid < sp.C ? sm.tile_cnt[tid] : 0;
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (unsigned)o) incl += t; }
+      if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+      __syncthreads();
+      uint32_t wb = 0;
+      for (uint32_t k = 0; k < (tid >> 5); ++k) wb += sm.warp_tot[k];
+      if (tid < sp.C) sm.tile_start[tid] = wb + incl - v;
+      if (tid == kSortTile - 1) sm.total = wb + incl;
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (uint32_t w = 0; w < kSortMaxW; ++w)
+        if (code[w] != kNoDigit) {
+          const uint32_t g = (pl.merged ? 0u : w * pl.B) + (code[w] & 0x7fffffffu);
+          const uint32_t b = g >> sp.fb, pos = sm.tile_start[b] + rank[w];
+          // merged: the entry addresses the precomputed multiple 2^(c*w) * P_i directly
+          sm.val[pos] = (uint32_t)(i + (pl.merged ? (size_t)w * pl.table_stride : 0)) | (code[w] & 0x80000000u);
+          sm.key[pos] = (uint16_t)(g & fmask);
+          sm.bin[pos] = (uint16_t)b;
+        }
+    }
+    __syncthreads();
+    const uint32_t total = sm.total;
+    for (uint32_t t = tid; t < total; t += kSortTile) {
+      const uint32_t b = sm.bin[t];
+      const uint32_t dst = sm.run_base[b] + (t - sm.tile_start[b]);
+      val1[dst] = sm.val[t];
+      key1[dst] = sm.key[t];
+    }
+    __syncthreads();
+    if (tid < sp.C) { sm.run_base[tid] += sm.tile_cnt[tid]; sm.tile_cnt[tid] = 0; }
+    __syncthreads();
+  }
+}
+
+// grid = C (one CTA per coarse bin), block = 1024.  bin b holds entries [base[b * NC], base[(b + 1) * NC]) of val1 / key1.
+// Writes hist[g], offsets[g] for its buckets, offsets[G] (last bin) and the final idx.
+__global__ void __launch_bounds__(1024, 1) msm_sort_fine(const uint32_t* __restrict__ val1, const uint16_t* __restrict__ key1, SortPlan sp, const uint32_t* __restrict__ base,
+                                                         uint32_t* __restrict__ hist, uint32_t* __restrict__ offsets, uint32_t* __restrict__ idx) {
+  __shared__ uint32_t fh[kSortMaxFine], cur[kSortMaxFine];
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t b = blockIdx.x, tid = threadIdx.x, F = 1u << sp.fb;
+  const uint32_t bs = __ldg(base + (size_t)b * sp.NC), be = __ldg(base + (size_t)(b + 1) * sp.NC);
+  for (uint32_t k = tid; k < F; k += 1024) fh[k] = 0;
+  __syncthreads();
+  for (uint32_t e = bs + tid; e < be; e += 1024) atomicAdd(&fh[key1[e]], 1u);
+  __syncthreads();
+  // exclusive scan of fh (F <= 2048: two keys per thread)
+  {
+    const uint32_t k0 = 2 * tid, k1 = 2 * tid + 1;
+    const uint32_t v0 = k0 < F ? fh[k0] : 0, v1 = k1 < F ? fh[k1] : 0;
+    uint32_t incl = v0 + v1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (unsigned)o) incl += t; }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (uint32_t k = 0; k < (tid >> 5); ++k) wb += warp_tot[k];
+    const uint32_t ex = wb + incl - v0 - v1;
+    const size_t g0 = (size_t)b * F + k0;
+    if (k0 < F) { cur[k0] = ex; if (g0 < sp.G) { offsets[g0] = bs + ex; hist[g0] = v0; } }
+    if (k1 < F) { cur[k1] = ex + v0; if (g0 + 1 < sp.G) { offsets[g0 + 1] = bs + ex + v0; hist[g0 + 1] = v1; } }
+    if (b == gridDim.x - 1 && tid == 0) offsets[sp.G] = be;  // total number of entries
+  }
+  __syncthreads();
+  for (uint32_t e = bs + tid; e < be; e += 1024) {
+    const uint32_t pos = atomicAdd(&cur[key1[e]], 1u);
+    idx[bs + pos] = val1[e];
+  }
+}
+
 // ---- exclusive scan of the histogram (G entries) ---------------------------------------------------------
 static constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
 
@@ -737,6 +956,30 @@ static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
   if (ctx->profiling) cudaEventRecord(ctx->ev[k], st);
 }
 
+// two-level sort of the (window,bucket) entries of n scalars: hist[G], offsets[G+1] and idx[M] come out exactly as the
+// legacy msm_hist / scan / msm_scatter sequence leaves them.  val1: W*n u32 scratch, key1: W*n u16 scratch, ctab: 2*(C*NC+1) u32.
+static int legacy_sort_knob() {
+  static int knob = -1;  // experiment knob B200ZK_SORT=legacy: the r1 sort (one global atomic per entry and phase)
+  if (knob < 0) { const char* e = getenv("B200ZK_SORT"); knob = (e && !strcmp(e, "legacy")) ? 1 : 0; }
+  return knob;
+}
+static int run_two_level_sort(b200zk_ctx* ctx, const void* d_scalars, size_t n, uint32_t flags, const MsmPlan& pl, const SortPlan& sp, uint32_t* hist, uint32_t* offsets,
+                              uint32_t* tsum, uint32_t* val1, uint16_t* key1, uint32_t* ctab, uint32_t* idx, cudaStream_t st, bool mark) {
+  const size_t Gc = (size_t)sp.C * sp.NC, tilesC = (Gc + kScanTile - 1) / kScanTile;
+  uint32_t *cnt = ctab, *base = ctab + Gc + 1;
+  if (!ctx->attr_sort) { B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortCoarseSmem))); ctx->attr_sort = true; }
+  B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, (Gc + 1) * 4, st));
+  B2_LAUNCH(ctx, msm_sort_count, sp.NC * kSortCountSub, kHistTile, 0, st, d_scalars, n, flags, pl, sp, cnt);
+  if (mark) phase_mark(ctx, 1, st);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tilesC, kScanThreads, 0, st, (const uint32_t*)cnt, (const uint32_t*)nullptr, Gc, 0u, 0u, tsum);
+  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tilesC);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tilesC, kScanThreads, 0, st, (const uint32_t*)cnt, (const uint32_t*)nullptr, Gc, 0u, 0u, (const uint32_t*)tsum, base, (uint32_t*)nullptr);
+  if (mark) phase_mark(ctx, 2, st);
+  B2_LAUNCH(ctx, msm_sort_coarse, sp.NC, kSortTile, sizeof(SortCoarseSmem), st, d_scalars, n, flags, pl, sp, (const uint32_t*)base, val1, key1);
+  B2_LAUNCH(ctx, msm_sort_fine, sp.C, 1024, 0, st, (const uint32_t*)val1, (const uint16_t*)key1, sp, (const uint32_t*)base, hist, offsets, idx);
+  return B200ZK_OK;
+}
+
 // ---- chunk-pipelined schedule --------------------------------------------------------------------------------
 // The sort (histogram / scan / scatter: L2-atomic and latency bound, the multiplier pipe idle) and the bucket
 // accumulation (multiplier-pipe bound, memory system idle) use disjoint resources, so for large n the points are
@@ -760,6 +1003,18 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
     B2_TRY(ensure(ctx, s.hist, G * 4)); B2_TRY(ensure(ctx, s.offsets, (G + 1) * 4)); B2_TRY(ensure(ctx, s.cursor, G * 4));
     B2_TRY(ensure(ctx, s.run_off, (G + 1) * 4)); B2_TRY(ensure(ctx, s.tsum, tiles * 4));
     B2_TRY(ensure(ctx, s.digits, Mk_max * 4)); B2_TRY(ensure(ctx, s.idx, Mk_max * 4));
+  }
+  // the two-level sort is planned for the chunk size (the last chunk may be shorter: re-planned per chunk below)
+  SortPlan sp0;
+  const bool two_level = !legacy_sort_knob() && make_sort_plan(chunk, pl, ctx->sm_count, &sp0);
+  if (two_level) {
+    const size_t Gc = (size_t)kSortMaxBins * (size_t)ctx->sm_count;  // upper bound of C * NC for any chunk
+    for (int sl = 0; sl < 2; ++sl) {
+      SortSlot& s = ctx->slot[sl];
+      B2_TRY(ensure(ctx, s.key, Mk_max * 2));
+      B2_TRY(ensure(ctx, s.ctab, 2 * (Gc + 1) * 4));
+      B2_TRY(ensure(ctx, s.tsum, std::max(tiles, (Gc + kScanTile - 1) / kScanTile) * 4));
+    }
   }
   B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));
   B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
@@ -790,17 +1045,25 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
     // ---- sort stream
     if (k >= 2) B2_CUDA(ctx, cudaStreamWaitEvent(ss, s.released, 0));
     if (h_scalars) B2_CUDA(ctx, cudaMemcpyAsync((void*)(dsc + lo * 32), (const uint8_t*)h_scalars + lo * 32, nk * 32, cudaMemcpyHostToDevice, ss));
-    B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, ss));
-    const unsigned sgrid = (unsigned)std::min<size_t>((nk + 255) / 256, (size_t)ctx->sm_count * 8);
-    B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, ss, (const void*)(dsc + lo * 32), nk, flags, pl, hist, digits);
-    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
-    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
-    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
+    SortPlan sp;
+    const bool tl = two_level && make_sort_plan(nk, pl, ctx->sm_count, &sp);
+    if (tl) {
+      B2_TRY(run_two_level_sort(ctx, (const void*)(dsc + lo * 32), nk, flags, pl, sp, hist, offsets, tsum, digits, (uint16_t*)s.key.p, (uint32_t*)s.ctab.p, idx, ss, false));
+    } else {
+      B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, ss));
+      const unsigned sgrid = (unsigned)std::min<size_t>((nk + 255) / 256, (size_t)ctx->sm_count * 8);
+      B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, ss, (const void*)(dsc + lo * 32), nk, flags, pl, hist, digits);
+      B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
+      B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
+      B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
+    }
     B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)offsets, G, L, 0u, tsum);
     B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
     B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)offsets, G, L, 0u, tsum, run_off, (uint32_t*)nullptr);
-    const unsigned wgrid = (unsigned)std::min<size_t>((nk * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
-    B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, ss, (const uint32_t*)digits, nk, pl, cursor, idx);
+    if (!tl) {
+      const unsigned wgrid = (unsigned)std::min<size_t>((nk * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
+      B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, ss, (const uint32_t*)digits, nk, pl, cursor, idx);
+    }
     B2_CUDA(ctx, cudaEventRecord(s.sorted, ss));
     // ---- accumulate stream (the caller's)
     B2_CUDA(ctx, cudaStreamWaitEvent(st, s.sorted, 0));
@@ -839,6 +1102,7 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
 template <class F>
 static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial,
                    uint32_t table_c, size_t table_stride, const void* h_scalars, int sort_mode) {
+  NvtxRange nvtx_msm(sizeof(F) > 32 ? "b200zk:g2_msm" : "b200zk:g1_msm");
   // sort_mode (b200zk_msm_multi_resident_device): 0 = ordinary call; 1 = one-shot schedule, the digit sort stays in
   // the workspaces; 2 = the sort of the previous call (same scalars, same plan) is reused: only the point-dependent
   // half of the MSM runs (run scan, accumulation, bucket reduction)
@@ -912,8 +1176,19 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   uint32_t* tsum = (uint32_t*)ctx->ws_blocksums.p;
   uint32_t* idx = (uint32_t*)ctx->ws_idx.p;
 
+  SortPlan sp;
+  const bool two_level = !legacy_sort_knob() && make_sort_plan(n, pl, ctx->sm_count, &sp);
+  if (two_level) {
+    B2_TRY(ensure(ctx, ctx->ws_key, M_max * 2));
+    B2_TRY(ensure(ctx, ctx->ws_ctab, (2 * ((size_t)sp.C * sp.NC + 1)) * 4));
+    B2_TRY(ensure(ctx, ctx->ws_blocksums, (std::max(tiles, ((size_t)sp.C * sp.NC + kScanTile - 1) / kScanTile)) * 4));
+    tsum = (uint32_t*)ctx->ws_blocksums.p;
+  }
   phase_mark(ctx, 0, st);
-  if (sort_mode != 2) {
+  nvtxRangePushA("b200zk:msm_sort");
+  if (sort_mode != 2 && two_level) {
+    B2_TRY(run_two_level_sort(ctx, d_scalars, n, flags, pl, sp, hist, offsets, tsum, (uint32_t*)ctx->ws_digits.p, (uint16_t*)ctx->ws_key.p, (uint32_t*)ctx->ws_ctab.p, idx, st, true));
+  } else if (sort_mode != 2) {
     B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
     const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
     uint32_t* digits = (uint32_t*)ctx->ws_digits.p;
@@ -929,7 +1204,9 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
     phase_mark(ctx, 1, st);
     phase_mark(ctx, 2, st);
   }
+  nvtxRangePop();
   phase_mark(ctx, 3, st);
+  NvtxRange nvtx_acc("b200zk:msm_accumulate+reduce");
   // batched-affine pair-summing rounds: each halves the entries the XYZZ accumulation has to fold
   const uint32_t* cur_off = offsets;
   const void* cur_pts = d_points;

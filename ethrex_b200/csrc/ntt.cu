@@ -415,6 +415,7 @@ int ntt_set_root(b200zk_ctx* ctx, const uint8_t* root_le) {
 }
 
 int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const uint8_t* coset_gen, cudaStream_t st) {
+  NvtxRange nvtx_ntt("b200zk:fr_ntt");
   if (log_n > 28) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: log_n > 28 (two-adicity of Fr)");
   if ((uintptr_t)d_data & 15) return fail(ctx, B200ZK_ERR_INVALID_ARG, "ntt: the device buffer must be 16-byte aligned");
   const size_t n = (size_t)1 << log_n;

@@ -474,6 +474,21 @@ void orc_fr_mul(const u64* a, const u64* b, u64* out, size_t n) {
 }
 
 // --- synthetic inputs
+// out[i] = (a[i]*b[i] - c[i]) * z : the pointwise step of the Groth16 quotient on the coset (all Montgomery limbs, z one element)
+void orc_fr_quotient(const u64* a, const u64* b, const u64* c, const u64* z, u64* out, size_t n, int threads) {
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+  Fr zz; memcpy(zz.v, z, 32);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; ++i) {
+    Fr x, y, w; memcpy(x.v, a + 4 * i, 32); memcpy(y.v, b + 4 * i, 32); memcpy(w.v, c + 4 * i, 32);
+    Fr r = (x * y - w) * zz;
+    memcpy(out + 4 * i, r.v, 32);
+  }
+}
 void orc_rand_fr(u64* out_canonical, u64 seed, u64 start, size_t n) {
 #pragma omp parallel for schedule(static) if (n >= 4096)
   for (size_t i = 0; i < n; ++i) rand_fr_canonical(seed, start + i, out_canonical + 4 * i);

@@ -128,6 +128,14 @@ def field_mul(field: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return out
 
 
+def fr_quotient(a: np.ndarray, b: np.ndarray, c: np.ndarray, zinv: int, threads: int = 0) -> np.ndarray:
+    """(a*b - c) * zinv element-wise; a, b, c Montgomery limbs, zinv an integer mod r"""
+    out = np.empty_like(a)
+    z = fr_to_mont(int_to_limbs(zinv).reshape(1, 4))
+    lib().orc_fr_quotient(_p(a), _p(b), _p(c), _p(z), _p(out), C.c_size_t(a.size // 4), C.c_int(_thr(threads)))
+    return out
+
+
 def g1_chain(n: int, k: int, d: int, threads: int = 0) -> np.ndarray:
     out = np.empty((n, 8), dtype=np.uint64)
     lib().orc_g1_chain(_p(out), C.c_size_t(n), _p(int_to_limbs(k)), _p(int_to_limbs(d)), C.c_int(_thr(threads)))

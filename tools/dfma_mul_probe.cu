@@ -226,6 +226,25 @@ __global__ void __launch_bounds__(256) k_mul52(const uint64_t* in, uint64_t* out
   }
   for (int k = 0; k < 5; ++k) out[i * 5 + k] = a.v[k] ^ b.v[k] ^ c.v[k] ^ d.v[k];
 }
+// the lazy product again under a 64-register cap (4 CTAs of 256 threads per SM instead of 3): is it occupancy?
+__global__ void __launch_bounds__(256, 4) k_mul52_r64(const uint64_t* in, uint64_t* out, int rep) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  F52 a, b, c, d;
+  for (int k = 0; k < 5; ++k) { a.v[k] = in[i * 20 + k] & M52; b.v[k] = in[i * 20 + 5 + k] & M52; c.v[k] = in[i * 20 + 10 + k] & M52; d.v[k] = in[i * 20 + 15 + k] & M52; }
+  a.v[4] &= (1ull << 45) - 1; b.v[4] &= (1ull << 45) - 1; c.v[4] &= (1ull << 45) - 1; d.v[4] &= (1ull << 45) - 1;
+  for (int r = 0; r < rep; ++r) { a = mul52<false>(a, b); c = mul52<false>(c, d); b = mul52<false>(b, a); d = mul52<false>(d, c); }
+  for (int k = 0; k < 5; ++k) out[i * 5 + k] = a.v[k] ^ b.v[k] ^ c.v[k] ^ d.v[k];
+}
+// two independent products per thread instead of four interleaved chains: fewer live registers, less ILP
+__global__ void __launch_bounds__(256) k_mul52_ilp2(const uint64_t* in, uint64_t* out, int rep) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  F52 a, b;
+  for (int k = 0; k < 5; ++k) { a.v[k] = in[i * 20 + k] & M52; b.v[k] = in[i * 20 + 5 + k] & M52; }
+  a.v[4] &= (1ull << 45) - 1; b.v[4] &= (1ull << 45) - 1;
+  for (int r = 0; r < 2 * rep; ++r) { a = mul52<false>(a, b); b = mul52<false>(b, a); }
+  for (int k = 0; k < 5; ++k) out[i * 5 + k] = a.v[k] ^ b.v[k];
+}
+
 template <int MODE>  // 0: Fq::mul, 1: Fq::sqr  (the shipped product, same harness)
 __global__ void __launch_bounds__(256) k_mul32(const uint64_t* in64, uint64_t* out64, int rep) {
   using b200zk::Fq;
@@ -306,6 +325,8 @@ int main(int argc, char** argv) {
   run("sqr32_field_cuh", k_mul32<1>);
   run("mul52_dfma canonical (<p)", k_mul52<0>);
   run("mul52_dfma lazy (<2p, no final subtraction)", k_mul52<1>);
+  run("mul52_dfma lazy, 64-register cap (4 CTAs/SM)", k_mul52_r64);
+  run("mul52_dfma lazy, 2 chains per thread", k_mul52_ilp2);
   run("sqr52_dfma canonical", k_mul52<2>);
   run("sqr52_dfma lazy", k_mul52<3>);
   return 0;
