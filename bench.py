@@ -182,6 +182,8 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     value = (1 << log_sample) / (ms / 1e3)
     ntt_rate, ntt_dt = cpu_ntt_sample(min(22, args.log_n))
+    one_log = min(log_sample, 17)
+    r1, dt1, _, _, _ = cpu_msm_sample(one_log, threads=1)  # ethrex's lockfile builds ark-ec WITHOUT rayon
     line = {
         "impl": "reference", "metric": "bn254_g1_msm_points_per_sec", "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -190,7 +192,10 @@ def run_reference(args):
                    "points_per_gpu": 1 << args.log_n, "total_points": args.gpus << args.log_n,
                    "reference_arm": f"rank 0 times a 2^{log_sample}-point slice of that workload per step on the host cores (points/s does not depend on the slice length beyond 2^20)"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": orc.num_threads(), "kind": "port",
-                         "sample": f"2^{log_sample}-point slice of the 2^{args.log_n} workload, Pippenger c={orc.lib().orc_msm_window(1 << log_sample)} (ark-ec rule), all host threads"},
+                         "sample": f"2^{log_sample}-point slice of the 2^{args.log_n} workload, Pippenger c={orc.lib().orc_msm_window(1 << log_sample)} (ark-ec rule), all host threads",
+                         "single_thread": {"value": r1, "unit": "points/s", "sample": f"2^{one_log} points, {dt1:.2f} s (the reference's lockfile configuration: ark-ec without rayon)"},
+                         "note": "the reference has no MSM of its own and its third-party ones cannot be built here (no cargo / go, sources not vendored): this is the "
+                                 "oracle port of ark-ec 0.5.0's Pippenger; it gets no precomputed window tables (ark has none), the GPU arm does (one-off, outside its timed region)"},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ntt": {"metric": "fr_ntt_elems_per_sec", "value": ntt_rate, "unit": "elements/s", "sample": f"2^{min(22, args.log_n)} forward, {ntt_dt:.3f} s"},
         "gpu_launches": 0,

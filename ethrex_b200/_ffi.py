@@ -25,6 +25,8 @@ NTT_CANONICAL = 1 << 6
 NTT_BE = 1 << 7
 G16_INPUTS_DEVICE = 1 << 8
 G16_H_COEFFS = 1 << 9
+SCALARS_RAW = 1 << 10
+POINTS_COMPRESSED = 1 << 11
 
 _vp, _sz, _u32, _u64, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
 _ctx = C.c_void_p
@@ -91,6 +93,9 @@ SIGNATURES = {
     "b200zk_last_msm_phase_ms": (_int, [_ctx, C.POINTER(C.c_float)]),
     "b200zk_set_profiling": (_int, [_ctx, _int]),
     "b200zk_msm_multi_resident_device": (_int, [_ctx, _vp, _sz, _vp, _sz, _u32, _vp, _vp, _vp]),
+    "b200zk_bls12_381_g1_bases_upload": (_int, [_ctx, _vp, _sz, _u32, C.POINTER(_u64)]),
+    "b200zk_bls12_381_g1_msm_resident": (_int, [_ctx, _u64, _vp, _sz, _u32, _vp]),
+    "b200zk_kzg_blob_to_commitment": (_int, [_ctx, _u64, _vp, _sz, _vp]),
     "b200zk_bn254_g1_add_batch": (_int, [_ctx, _vp, _vp, _sz, _vp, _vp]),
     "b200zk_bn254_g1_mul_batch": (_int, [_ctx, _vp, _vp, _sz, _vp, _vp]),
     "b200zk_bn254_pairing_check_batch": (_int, [_ctx, _vp, _vp, _sz, _vp, _vp]),

@@ -292,6 +292,34 @@ class Context:
         cg = C.cast(C.c_char_p(coset_gen), C.c_void_p) if coset_gen is not None else None
         self._check(F.lib.b200zk_fr_ntt_device(self._h, _dev_ptr(d_data), log_n, flags, cg, _current_stream_ptr(self.device)), "b200zk_fr_ntt_device")
 
+    # ------------------------------------------------------------------ BLS12-381 G1 / EIP-4844 blob commitments
+    def bls12_381_g1_bases_upload(self, points, n: int, flags: int = F.POINTS_COMPRESSED) -> int:
+        """points: n x 48 bytes compressed (default, the trusted setup's form) or n x 96 bytes uncompressed (flags=0)"""
+        _need(points, n * (48 if flags & F.POINTS_COMPRESSED else 96), "b200zk_bls12_381_g1_bases_upload points")
+        pp, keep = _host_ptr(points)
+        h = C.c_uint64()
+        self._check(F.lib.b200zk_bls12_381_g1_bases_upload(self._h, pp, n, flags, C.byref(h)), "b200zk_bls12_381_g1_bases_upload")
+        return h.value
+
+    def bls12_381_g1_msm_resident(self, handle: int, scalars, n: int, flags: int = F.SCALARS_BE) -> bytes:
+        """-> 48 bytes compressed; scalars 32-byte big-endian (default) or little-endian limbs, each < the group order"""
+        _need(scalars, 32 * n, "b200zk_bls12_381_g1_msm_resident scalars")
+        sp, keep = _host_ptr(scalars)
+        out = C.create_string_buffer(48)
+        self._check(F.lib.b200zk_bls12_381_g1_msm_resident(self._h, handle, sp, n, flags, out), "b200zk_bls12_381_g1_msm_resident")
+        return out.raw
+
+    def kzg_blob_to_commitment(self, setup_handle: int, blobs) -> list:
+        """blobs: bytes-like of k x 131072 bytes (4096 x 32-byte big-endian field elements each) -> [48-byte commitments]"""
+        total = _host_len(blobs)
+        if total % (4096 * 32):
+            raise B200Error.serialization("a blob is 4096 x 32 bytes")
+        k = total // (4096 * 32)
+        bp, keep = _host_ptr(blobs)
+        out = C.create_string_buffer(max(1, 48 * k))
+        self._check(F.lib.b200zk_kzg_blob_to_commitment(self._h, setup_handle, bp, k, out), "b200zk_kzg_blob_to_commitment")
+        return [out.raw[48 * i:48 * i + 48] for i in range(k)]
+
     # ------------------------------------------------------------------ NTT root of unity (SURVEY.md section 8c)
     NTT_ROOT_ARK, NTT_ROOT_HALO2 = 0, 1
 

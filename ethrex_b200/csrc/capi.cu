@@ -4,6 +4,7 @@
 // status); the trait these calls sit behind is ProverBackend
 // (/root/reference/crates/prover/src/backend/mod.rs:81-147).
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -95,7 +96,7 @@ template <bool G2>
 int msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, uint8_t* out) {
   if (!ctx || !out || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: null argument");
   auto it = ctx->bases.find(handle);
-  if (it == ctx->bases.end() || it->second.g2 != G2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: unknown handle");
+  if (it == ctx->bases.end() || it->second.g2 != G2 || it->second.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident: n exceeds the resident bases");
   // host scalars go straight into the (chunk-pipelined) schedule: their upload overlaps the previous chunk's work
   return msm_device<G2>(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, ctx->stream, out, it->second.table_c, it->second.n, scalars);
@@ -105,7 +106,7 @@ template <bool G2>
 int msm_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, uint8_t* out) {
   if (!ctx || !out || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: null argument");
   auto it = ctx->bases.find(handle);
-  if (it == ctx->bases.end() || it->second.g2 != G2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: unknown handle");
+  if (it == ctx->bases.end() || it->second.g2 != G2 || it->second.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_resident_device: n exceeds the resident bases");
   return msm_device<G2>(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, stream, out, it->second.table_c, it->second.n);
 }
@@ -184,10 +185,20 @@ int b200zk_init(int device, b200zk_ctx** out) {
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   {
+    // The accumulation gathers 64-byte affine points at random: with the default L2 fetch granularity every gather pulls
+    // 128 bytes out of HBM (ncu r1c: 29.3 GB read per 2^24 MSM against 14.8 GB of gathers).  A 64-byte granularity is
+    // all this library's access patterns need (every stream it reads is either contiguous or 64/128-byte records).
+    // The limit is a per-device hint; B200ZK_L2_FETCH=0 leaves the device default, 32 / 64 / 128 set it explicitly.
+    const char* e = getenv("B200ZK_L2_FETCH");
+    const int want = e ? atoi(e) : 64;
+    if (want == 32 || want == 64 || want == 128) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want) != cudaSuccess) cudaGetLastError(); }
+  }
+  {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
     if (cudaStreamCreateWithPriority(&ctx->stream_sort, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); b200zk_destroy(ctx); return B200ZK_ERR_CUDA; }
     cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
+    for (auto& e : ctx->ev_up) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto& sl : ctx->slot) { cudaEventCreateWithFlags(&sl.sorted, cudaEventDisableTiming); cudaEventCreateWithFlags(&sl.released, cudaEventDisableTiming); }
   }
   *out = ctx;
@@ -216,6 +227,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
     if (sl.released) cudaEventDestroy(sl.released);
   }
   if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+  for (auto& e : ctx->ev_up) if (e) cudaEventDestroy(e);
   if (ctx->stream_sort) cudaStreamDestroy(ctx->stream_sort);
   for (auto& kv : ctx->twiddles) { cudaFree(kv.second.d); if (kv.second.ready) cudaEventDestroy(kv.second.ready); }
   for (auto& kv : ctx->bases) cudaFree(kv.second.d);
@@ -293,12 +305,13 @@ int b200zk_bases_precompute(b200zk_ctx* ctx, uint64_t handle, uint32_t window_bi
   BasesEntry& e = it->second;
   if (e.table_c) return fail(ctx, B200ZK_ERR_INVALID_ARG, "bases_precompute: handle already precomputed");
   const uint32_t c = window_bits ? window_bits : precompute_window(e.n);
-  const uint32_t W = (255 + c - 1) / c;
-  const size_t pt = e.g2 ? 128 : 64;
+  const uint32_t W = ((e.bls ? 256u : 255u) + c - 1) / c;  // ScalarBits<F>: BLS12-381's group order has one more bit
+  const size_t pt = e.bls ? 96 : (e.g2 ? 128 : 64);
   if ((unsigned long long)e.n * W >= (1ull << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "bases_precompute: table exceeds 31-bit indices");
   void* table = nullptr;
   B2_CUDA(ctx, cudaMalloc(&table, (size_t)W * e.n * pt + 32));
-  int rc = e.g2 ? msm_precompute_g2(ctx, e.d, e.n, c, table, ctx->stream) : msm_precompute_g1(ctx, e.d, e.n, c, table, ctx->stream);
+  int rc = e.bls ? msm_precompute_bls(ctx, e.d, e.n, c, table, ctx->stream)
+                 : (e.g2 ? msm_precompute_g2(ctx, e.d, e.n, c, table, ctx->stream) : msm_precompute_g1(ctx, e.d, e.n, c, table, ctx->stream));
   cudaError_t ce = cudaStreamSynchronize(ctx->stream);
   if (rc > B200ZK_OK_INFINITY || ce != cudaSuccess) { cudaFree(table); return rc > B200ZK_OK_INFINITY ? rc : fail(ctx, B200ZK_ERR_CUDA, "bases_precompute", ce); }
   cudaFree(e.d);
@@ -370,7 +383,7 @@ int b200zk_g2_msm_partial_device(b200zk_ctx* ctx, const void* d_points, const vo
 int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial128 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
-  if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (it == ctx->bases.end() || it->second.g2 || it->second.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g1(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n);
 }
@@ -378,21 +391,21 @@ int b200zk_g1_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, cons
 int b200zk_g1_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial128) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial128 || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
-  if (it == ctx->bases.end() || it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (it == ctx->bases.end() || it->second.g2 || it->second.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g1(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial128, it->second.table_c, it->second.n, scalars);
 }
 int b200zk_g2_msm_partial_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial256 || (!scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
-  if (it == ctx->bases.end() || !it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (it == ctx->bases.end() || !it->second.g2 || it->second.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g2(ctx, it->second.d, nullptr, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial256, it->second.table_c, it->second.n, scalars);
 }
 int b200zk_g2_msm_partial_resident_device(b200zk_ctx* ctx, uint64_t handle, const void* d_scalars, size_t n, uint32_t flags, void* stream, void* d_partial256) { b200zk::DeviceGuard guard(ctx);
   if (!ctx || !d_partial256 || (!d_scalars && n)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: null argument");
   auto it = ctx->bases.find(handle);
-  if (it == ctx->bases.end() || !it->second.g2) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
+  if (it == ctx->bases.end() || !it->second.g2 || it->second.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: unknown handle");
   if (n > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_partial_resident: n exceeds the resident bases");
   return msm_run_g2(ctx, it->second.d, d_scalars, n, flags & ~B200ZK_POINTS_BE, pick_stream(ctx, stream), d_partial256, it->second.table_c, it->second.n);
 }
@@ -411,6 +424,7 @@ int b200zk_msm_multi_resident_device(b200zk_ctx* ctx, const uint64_t* handles, s
     if (it == ctx->bases.end()) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: unknown handle");
     const BasesEntry& e = it->second;
     if (n > e.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: n exceeds the resident bases");
+    if (e.bls) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm_multi_resident_device: BLS12-381 bases in a BN254 call");
     if (!first) first = &e;
     // one sort serves every column only if they share the plan: same window tables (or none) over the same point count
     if (e.table_c != first->table_c || (e.table_c && e.n != first->n))

@@ -10,8 +10,13 @@
 
 #include "../../include/b200zk.h"
 #include "curve.cuh"
+#include "bls381.cuh"
 
 namespace b200zk {
+
+template <> struct CurveB<Fp381> {
+  static B2_D Fp381 b() { Fp381 four = Fp381::zero(); four.v[0] = 4; return Fp381::to_mont(four); }  // y^2 = x^3 + 4
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -35,6 +40,7 @@ struct BasesEntry {
   void* d = nullptr;
   size_t n = 0;
   bool g2 = false;
+  bool bls = false;      // BLS12-381 G1 points (Fp381 Montgomery, 96 B affine): the KZG trusted setup
   uint32_t table_c = 0;  // != 0: d holds W = ceil(255/c) windows of n points: 2^(c*w) * P_i at w*n + i
 };
 
@@ -50,6 +56,7 @@ struct b200zk_ctx {
   uint32_t msm_chunks = 0;   // chunk count of the pipelined MSM schedule; 0 = automatic
   cudaStream_t stream_sort = nullptr;  // high-priority stream the sort of chunk k+1 runs on while chunk k accumulates
   cudaEvent_t ev_in = nullptr;
+  cudaEvent_t ev_up[64] = {};  // upload k of the chunk-pipelined MSM has landed (recorded on stream_sort, waited on by the caller's stream)
   b200zk::SortSlot slot[2];
   b200zk::DevBuf ws_totals, ws_bitpart;
   b200zk::DevBuf ws_key, ws_ctab;  // two-level sort: 16-bit fine keys of the coarse-partitioned entries; per-(bin, CTA) counts / bases
@@ -176,6 +183,26 @@ B2_D Fq2 load_field_nc(const void* base, size_t slot, const Fq2*) { return {load
 B2_D void store_field(void* base, size_t slot, const Fq& a) { store_fe<Fq>(base, slot, a); }
 B2_D void store_field(void* base, size_t slot, const Fq2& a) { store_fe<Fq>(base, 2 * slot, a.c0); store_fe<Fq>(base, 2 * slot + 1, a.c1); }
 
+// 48-byte (Fp381) elements: three 128-bit words
+B2_D Fp381 load_field(const void* base, size_t slot, const Fp381*) {
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 3 * slot;
+  uint4 a = p[0], b = p[1], c = p[2];
+  Fp381 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w; r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+  return r;
+}
+B2_D Fp381 load_field_nc(const void* base, size_t slot, const Fp381*) {
+  const uint4* p = reinterpret_cast<const uint4*>(base) + 3 * slot;
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+  Fp381 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w; r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+  return r;
+}
+B2_D void store_field(void* base, size_t slot, const Fp381& a) {
+  uint4* p = reinterpret_cast<uint4*>(base) + 3 * slot;
+  p[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); p[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]); p[2] = make_uint4(a.v[8], a.v[9], a.v[10], a.v[11]);
+}
+
 template <class F> B2_D Affine<F> load_affine_nc(const void* base, size_t i) {
   return {load_field_nc(base, 2 * i, (const F*)nullptr), load_field_nc(base, 2 * i + 1, (const F*)nullptr)};
 }
@@ -192,12 +219,25 @@ template <class F> B2_D void store_xyzz(void* base, size_t i, const XYZZ<F>& p) 
 template <class F> struct FieldBytes;
 template <> struct FieldBytes<Fq> { static constexpr size_t value = 32; };
 template <> struct FieldBytes<Fq2> { static constexpr size_t value = 64; };
+template <> struct FieldBytes<Fp381> { static constexpr size_t value = 48; };
+template <class F> struct ScalarBits { static constexpr uint32_t value = 255; };  // BN254: r < 2^254, + 1 for the recoding's carry
+template <> struct ScalarBits<Fp381> { static constexpr uint32_t value = 256; };     // BLS12-381: r < 2^255
+template <class F> struct IsFq2 { static constexpr bool value = false; };
+template <> struct IsFq2<Fq2> { static constexpr bool value = true; };
 
 // internal cross-TU entry points
 // table_c != 0: d_points is a precomputed window table with `table_stride` points per window
 // h_scalars != nullptr: the scalars are in (pinned) host memory and are uploaded chunk by chunk inside the pipeline
 int msm_run_g1(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr, int sort_mode = 0);
 int msm_run_g2(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr, int sort_mode = 0);
+int msm_run_bls(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial, uint32_t table_c = 0, size_t table_stride = 0, const void* h_scalars = nullptr, int sort_mode = 0);
+int msm_precompute_bls(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st);
+int msm_encode_bls(b200zk_ctx* ctx, const void* d_partials, size_t count, uint32_t flags, cudaStream_t st, void* d_out);
+// compressed (48 B, ZCash format) or uncompressed (96 B big-endian x | y) G1 points -> native affine; status[0] = first index with a coordinate >= p,
+// status[1] = first index not on the curve / with malformed flag bits (each n when none)
+int bls_points_to_native(b200zk_ctx* ctx, const void* d_in, void* d_native, size_t n, bool compressed, cudaStream_t st);
+// first index of a 32-byte big-endian scalar >= the BLS12-381 group order among n, or n
+int bls_scalars_check(b200zk_ctx* ctx, const void* d_scalars_be, size_t n, cudaStream_t st, size_t* bad_index);
 int msm_precompute_g1(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st);
 int msm_precompute_g2(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st);
 uint32_t precompute_window(size_t n);

@@ -35,7 +35,7 @@ int groth16_commit_partials(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, const 
   for (int k = 0; k < 5; ++k) {
     if (!pk->handle[k]) { if (k == 1) continue; return fail(ctx, B200ZK_ERR_INVALID_ARG, "groth16_commit: only the B_g1 column may be absent"); }
     auto it = ctx->bases.find(pk->handle[k]);
-    if (it == ctx->bases.end() || it->second.g2 != (k == 2)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "groth16_commit: unknown handle or wrong group for a column");
+    if (it == ctx->bases.end() || it->second.bls || it->second.g2 != (k == 2)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "groth16_commit: unknown handle or wrong group for a column");
     if (pk->count[k] > it->second.n) return fail(ctx, B200ZK_ERR_INVALID_ARG, "groth16_commit: a column count exceeds its resident bases");
     col[k] = &it->second;
     if (k < 4 && pk->offset[k] + pk->count[k] > wit_end) wit_end = pk->offset[k] + pk->count[k];

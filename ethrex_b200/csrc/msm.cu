@@ -27,6 +27,7 @@
 namespace b200zk {
 
 static constexpr int kMaxWindows = 64;
+static constexpr uint32_t kMaxPipelineChunks = 64;  // = events in b200zk_ctx::ev_up
 static constexpr int kChunk = 16;  // buckets per running-sum chunk (measured 8/16/32/64: profiles/r1h_g2.md)
 static constexpr int kG2MinBlocks = 1;  // register cap of msm_accumulate<Fq2> (see the launch site)
 
@@ -50,7 +51,9 @@ uint32_t precompute_window(size_t n) {
   return lg;
 }
 
-static MsmPlan make_plan(size_t n, uint32_t forced_c) {
+// scalar_bits: bits the signed-digit recoding must cover = bit length of the group order + 1 (the top window absorbs the
+// last carry): 255 for BN254 (r < 2^254), 256 for BLS12-381 (r < 2^255)
+static MsmPlan make_plan(size_t n, uint32_t forced_c, uint32_t scalar_bits = 255) {
   uint32_t lg = 0;
   while (((size_t)1 << lg) < n) ++lg;
   // measured on B200 (profiles/): c = 16 is best for 2^18..2^22 points, 17 from 2^23 up; below that lg-4
@@ -60,7 +63,7 @@ static MsmPlan make_plan(size_t n, uint32_t forced_c) {
   if (c > 24) c = 24;
   MsmPlan p;
   p.c = c;
-  p.W = (255 + c - 1) / c;
+  p.W = (scalar_bits + c - 1) / c;
   p.B = 1u << (c - 1);
   static int chunk_knob = -1;  // experiment knob B200ZK_CHUNK=8|16|32|64: buckets per running-sum chunk
   if (chunk_knob < 0) { const char* e = getenv("B200ZK_CHUNK"); chunk_knob = e ? atoi(e) : 0; if (chunk_knob & (chunk_knob - 1)) chunk_knob = 0; }
@@ -86,7 +89,9 @@ B2_D void decode_scalar(uint4 lo, uint4 hi, uint32_t flags, uint32_t s[8]) {
   Fr f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) f.v[k] = s[k];
-  if (flags & B200ZK_SCALARS_MONT) {
+  if (flags & B200ZK_SCALARS_RAW) {
+    // another group's scalars (BLS12-381): no reduction; the caller guarantees < 2^255 (validated by bls_scalars_check)
+  } else if (flags & B200ZK_SCALARS_MONT) {
     // a Montgomery residue may be any value < 2^256 only if malformed; reduce first so mul's bound holds
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
@@ -94,7 +99,7 @@ B2_D void decode_scalar(uint4 lo, uint4 hi, uint32_t flags, uint32_t s[8]) {
       if (!borrow) f = t;
     }
     f = Fr::from_mont(f);
-  } else {
+  } else if (f.v[7] >= FrCfg::mod(7)) {  // top limb below r's: already canonical (every reduced scalar) -- skip the loop
     // 2^256 / r < 6: at most five subtractions bring any 256-bit value below r
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
 //   (scan)           exclusive scan of cnt in (bin, cta) order: every (bin, cta) pair owns a private, contiguous output run
 //   msm_sort_coarse  the same CTA walks the same scalars in tiles of 1024; a tile's entries are ranked per bin with
 //                    shared-memory atomics, permuted in shared memory, and copied out so that adjacent lanes write adjacent
-//                    addresses (value u32 + fine key u16) -- no global atomics, runs instead of scattered stores
+//                    addresses (one 8-byte word per entry: value | fine key) -- no global atomics, runs instead of scattered stores
 //   msm_sort_fine    one CTA per coarse bin: fine histogram in shared memory (-> the bucket offsets and counts the
 //                    accumulation needs, for free), then the final placement with shared-memory cursors; the bin's output
 //                    region is a few MB, so its 4-byte stores combine in L2
@@ -250,7 +255,8 @@ static constexpr uint32_t kSortTile = 1024;        // scalars per coarse tile = 
 static constexpr uint32_t kSortMaxW = 16;          // windows per scalar the staging buffers are sized for (c >= 16)
 static constexpr uint32_t kSortMaxBins = 1024;     // coarse bins
 static constexpr uint32_t kSortMaxFine = 2048;     // fine keys per bin
-static constexpr uint32_t kSortCountSub = 4;       // msm_sort_count CTAs per coarse CTA range
+static constexpr uint32_t kSortCountSub = 4;
+static constexpr int kFineIlp = 8;               // independent (key, value) loads in flight per thread of msm_sort_fine       // msm_sort_count CTAs per coarse CTA range
 
 struct SortPlan {
   uint32_t fb;        // fine bits
@@ -340,15 +346,14 @@ __global__ void __launch_bounds__(kHistTile) msm_sort_count(const void* scalars,
 
 // grid = NC, block = kSortTile.  base[bin * NC + r] = first output slot of (bin, range r).
 struct SortCoarseSmem {
-  uint32_t val[kSortTile * kSortMaxW];
-  uint16_t key[kSortTile * kSortMaxW];
-  uint16_t bin[kSortTile * kSortMaxW];
+  uint2 ent[kSortTile * kSortMaxW];     // staged entry: x = value (point index | sign << 31), y = fine key
+  uint32_t dst[kSortTile * kSortMaxW];  // its slot in the coarse-partitioned array
   uint32_t run_base[kSortMaxBins], tile_cnt[kSortMaxBins], tile_start[kSortMaxBins];
   uint32_t warp_tot[kSortTile / 32];
   uint32_t total;
 };
 __global__ void __launch_bounds__(kSortTile, 1) msm_sort_coarse(const void* __restrict__ scalars, size_t n, uint32_t flags, MsmPlan pl, SortPlan sp, const uint32_t* __restrict__ base,
-                                                               uint32_t* __restrict__ val1, uint16_t* __restrict__ key1) {
+                                                               uint2* __restrict__ ent1) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SortCoarseSmem& sm = *reinterpret_cast<SortCoarseSmem*>(smem_raw);
   const uint32_t r = blockIdx.x, tid = threadIdx.x;
@@ -396,58 +401,97 @@ __global__ void __launch_bounds__(kSortTile, 1) msm_sort_coarse(const void* __re
           const uint32_t g = (pl.merged ? 0u : w * pl.B) + (code[w] & 0x7fffffffu);
           const uint32_t b = g >> sp.fb, pos = sm.tile_start[b] + rank[w];
           // merged: the entry addresses the precomputed multiple 2^(c*w) * P_i directly
-          sm.val[pos] = (uint32_t)(i + (pl.merged ? (size_t)w * pl.table_stride : 0)) | (code[w] & 0x80000000u);
-          sm.key[pos] = (uint16_t)(g & fmask);
-          sm.bin[pos] = (uint16_t)b;
+          sm.ent[pos] = make_uint2((uint32_t)(i + (pl.merged ? (size_t)w * pl.table_stride : 0)) | (code[w] & 0x80000000u), g & fmask);
+          sm.dst[pos] = sm.run_base[b] + rank[w];
         }
     }
     __syncthreads();
     const uint32_t total = sm.total;
-    for (uint32_t t = tid; t < total; t += kSortTile) {
-      const uint32_t b = sm.bin[t];
-      const uint32_t dst = sm.run_base[b] + (t - sm.tile_start[b]);
-      val1[dst] = sm.val[t];
-      key1[dst] = sm.key[t];
-    }
+    for (uint32_t t = tid; t < total; t += kSortTile) ent1[sm.dst[t]] = sm.ent[t];  // adjacent t: same bin's run, adjacent slots
     __syncthreads();
     if (tid < sp.C) { sm.run_base[tid] += sm.tile_cnt[tid]; sm.tile_cnt[tid] = 0; }
     __syncthreads();
   }
 }
 
-// grid = C (one CTA per coarse bin), block = 1024.  bin b holds entries [base[b * NC], base[(b + 1) * NC]) of val1 / key1.
+// grid = C (one CTA per coarse bin), block = 1024.  bin b holds entries [base[b * NC], base[(b + 1) * NC]) of ent1.
 // Writes hist[g], offsets[g] for its buckets, offsets[G] (last bin) and the final idx.
-__global__ void __launch_bounds__(1024, 1) msm_sort_fine(const uint32_t* __restrict__ val1, const uint16_t* __restrict__ key1, SortPlan sp, const uint32_t* __restrict__ base,
+// The placement is staged like the coarse pass: a tile of kFineTile entries is ranked per key in shared memory, permuted
+// there, and copied out so that the entries of one bucket leave as one run (ncu r2d of the direct version -- one scattered
+// 4-byte store per entry -- showed the L2 tag lookups as the limit: lts__t_tag_requests 47 % at 2.2 ms).
+static constexpr uint32_t kFineTile = 8192;  // entries per tile = 8 per thread
+struct SortFineSmem {
+  uint32_t val[kFineTile], dst[kFineTile];
+  uint32_t fh[kSortMaxFine], cur[kSortMaxFine], tcnt[kSortMaxFine], tstart[kSortMaxFine];
+  uint32_t warp_tot[32];
+  uint32_t total;
+};
+// exclusive scan of in[0..F) (F <= 2048, two keys per thread of a 1024-thread CTA) into out; returns nothing, leaves the grand total in *total
+B2_D void scan_fine_keys(const uint32_t* in, uint32_t* out, uint32_t F, uint32_t* warp_tot, uint32_t* total) {
+  const uint32_t tid = threadIdx.x, k0 = 2 * tid, k1 = 2 * tid + 1;
+  const uint32_t v0 = k0 < F ? in[k0] : 0, v1 = k1 < F ? in[k1] : 0;
+  uint32_t incl = v0 + v1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (unsigned)o) incl += t; }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t wb = 0;
+  for (uint32_t k = 0; k < (tid >> 5); ++k) wb += warp_tot[k];
+  const uint32_t ex = wb + incl - v0 - v1;
+  if (k0 < F) out[k0] = ex;
+  if (k1 < F) out[k1] = ex + v0;
+  if (tid == 1023) *total = wb + incl;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(1024, 1) msm_sort_fine(const uint2* __restrict__ ent1, SortPlan sp, const uint32_t* __restrict__ base,
                                                          uint32_t* __restrict__ hist, uint32_t* __restrict__ offsets, uint32_t* __restrict__ idx) {
-  __shared__ uint32_t fh[kSortMaxFine], cur[kSortMaxFine];
-  __shared__ uint32_t warp_tot[32];
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SortFineSmem& sm = *reinterpret_cast<SortFineSmem*>(smem_raw);
   const uint32_t b = blockIdx.x, tid = threadIdx.x, F = 1u << sp.fb;
   const uint32_t bs = __ldg(base + (size_t)b * sp.NC), be = __ldg(base + (size_t)(b + 1) * sp.NC);
-  for (uint32_t k = tid; k < F; k += 1024) fh[k] = 0;
+  for (uint32_t k = tid; k < F; k += 1024) { sm.fh[k] = 0; sm.tcnt[k] = 0; }
   __syncthreads();
-  for (uint32_t e = bs + tid; e < be; e += 1024) atomicAdd(&fh[key1[e]], 1u);
-  __syncthreads();
-  // exclusive scan of fh (F <= 2048: two keys per thread)
-  {
-    const uint32_t k0 = 2 * tid, k1 = 2 * tid + 1;
-    const uint32_t v0 = k0 < F ? fh[k0] : 0, v1 = k1 < F ? fh[k1] : 0;
-    uint32_t incl = v0 + v1;
+  // ---- histogram of the bin's fine keys (kFineIlp independent loads in flight per thread)
+  for (uint32_t e0 = bs + tid; e0 < be; e0 += 1024 * kFineIlp) {
+    uint32_t kk[kFineIlp];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (unsigned)o) incl += t; }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    uint32_t wb = 0;
-    for (uint32_t k = 0; k < (tid >> 5); ++k) wb += warp_tot[k];
-    const uint32_t ex = wb + incl - v0 - v1;
-    const size_t g0 = (size_t)b * F + k0;
-    if (k0 < F) { cur[k0] = ex; if (g0 < sp.G) { offsets[g0] = bs + ex; hist[g0] = v0; } }
-    if (k1 < F) { cur[k1] = ex + v0; if (g0 + 1 < sp.G) { offsets[g0 + 1] = bs + ex + v0; hist[g0 + 1] = v1; } }
-    if (b == gridDim.x - 1 && tid == 0) offsets[sp.G] = be;  // total number of entries
+    for (int u = 0; u < kFineIlp; ++u) { const uint32_t e = e0 + u * 1024; kk[u] = e < be ? __ldg(&ent1[e].y) : 0xffffffffu; }
+#pragma unroll
+    for (int u = 0; u < kFineIlp; ++u) if (kk[u] != 0xffffffffu) atomicAdd(&sm.fh[kk[u]], 1u);
   }
   __syncthreads();
-  for (uint32_t e = bs + tid; e < be; e += 1024) {
-    const uint32_t pos = atomicAdd(&cur[key1[e]], 1u);
-    idx[bs + pos] = val1[e];
+  scan_fine_keys(sm.fh, sm.cur, F, sm.warp_tot, &sm.total);  // cur[k] = first slot (relative to bs) of key k
+  for (uint32_t k = tid; k < F; k += 1024) {
+    const size_t g = (size_t)b * F + k;
+    if (g < sp.G) { offsets[g] = bs + sm.cur[k]; hist[g] = sm.fh[k]; }
+  }
+  if (b == gridDim.x - 1 && tid == 0) offsets[sp.G] = be;  // total number of entries
+  // ---- placement, tile by tile
+  for (uint32_t t0 = bs; t0 < be; t0 += kFineTile) {
+    uint2 ev[kFineTile / 1024];
+    uint32_t rank[kFineTile / 1024];
+#pragma unroll
+    for (int u = 0; u < (int)(kFineTile / 1024); ++u) {
+      const uint32_t e = t0 + u * 1024 + tid;
+      ev[u] = e < be ? __ldg(ent1 + e) : make_uint2(0u, 0xffffffffu);
+    }
+#pragma unroll
+    for (int u = 0; u < (int)(kFineTile / 1024); ++u) rank[u] = ev[u].y != 0xffffffffu ? atomicAdd(&sm.tcnt[ev[u].y], 1u) : 0u;
+    __syncthreads();
+    scan_fine_keys(sm.tcnt, sm.tstart, F, sm.warp_tot, &sm.total);
+#pragma unroll
+    for (int u = 0; u < (int)(kFineTile / 1024); ++u)
+      if (ev[u].y != 0xffffffffu) {
+        const uint32_t pos = sm.tstart[ev[u].y] + rank[u];
+        sm.val[pos] = ev[u].x;
+        sm.dst[pos] = bs + sm.cur[ev[u].y] + rank[u];
+      }
+    __syncthreads();
+    const uint32_t total = sm.total;
+    for (uint32_t t = tid; t < total; t += 1024) idx[sm.dst[t]] = sm.val[t];  // adjacent t: one bucket's run, adjacent slots
+    __syncthreads();
+    for (uint32_t k = tid; k < F; k += 1024) { sm.cur[k] += sm.tcnt[k]; sm.tcnt[k] = 0; }
+    __syncthreads();
   }
 }
 
@@ -610,6 +654,173 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const void* __restri
   }
   store_xyzz(partials, slot, acc);
   run_bucket[slot] = g;
+}
+
+// ---- G2 accumulation on lane pairs -----------------------------------------------------------------------------
+// msm_accumulate<Fq2> keeps an XYZZ accumulator over Fq2 (64 registers), the point and its prefetch (2 x 32) and the
+// temporaries of an Fq2 product in ONE thread: 255 registers, 2 CTAs (8 warps) per SM, ~74 % of the multiplier ceiling
+// (r2c bench).  Here two adjacent lanes share one slice: lane 2k holds the real component (c0) of every Fq2 value,
+// lane 2k+1 the imaginary one (c1) -- half the registers per thread, the occupancy of the G1 kernel -- and the
+// components an Fq2 product needs from the partner lane travel by SHFL.XOR 1 (8 shuffles per value, ~90 per mixed
+// addition against ~1800 wide multiplies per lane).  Every product stays a shared-reduction form of field.cuh:
+//   (a b).c0 = a0 b0 + (-a1) b1      (a b).c1 = a1 b0 + a0 b1            one mul2_add per lane
+//   (a^2).c0 = (a0 + a1)(a0 - a1)    (a^2).c1 = (2 a1) a0                one mul per lane
+//   (a b - c d).c0 / .c1                                                  one mul4_add per lane
+// Operands are chosen with selects on the lane's role, so both lanes run the same instruction stream; pair-uniform
+// branches (identity, doubling, cancellation) are decided on both components with one more shuffle.  Memory layout,
+// slice scheme and run numbering are those of msm_accumulate: the other kernels do not know the difference.
+// The three products of the lane-pair kernel as REAL functions (arguments and result travel in registers: checked in SASS,
+// no local-memory traffic).  Inlined, one G2 mixed addition is ~3500 SASS instructions = 56 KB and the loop body does not
+// fit the instruction cache (ncu r2g: stall_no_instruction 1.2 per issue, the top stall); as calls the body is ~13 KB plus
+// ~13 KB of callees, the size of the G1 kernel's body.
+// A call is a scheduling barrier, so a callee that computes ONE product leaves the multiplier pipe with a single carry
+// chain per warp (measured: no faster than the inlined body).  The callees therefore compute the TWO independent products
+// the XYZZ formulas offer at every step (U2 | S2, PP | R^2, PPP | Q, ZZ3 | ZZZ3): two interleaved chains per warp, like
+// the G1 kernel.
+struct FqPair { Fq r0, r1; };
+__device__ __noinline__ FqPair fq_mul_x2_call(Fq a, Fq b, Fq c, Fq d) { return {Fq::mul(a, b), Fq::mul(c, d)}; }
+__device__ __noinline__ FqPair fq_mul2_add_x2_call(Fq a, Fq b, Fq c, Fq d, Fq e, Fq f, Fq g, Fq h) { return {Fq::mul2_add(a, b, c, d), Fq::mul2_add(e, f, g, h)}; }
+__device__ __noinline__ Fq fq_mul2_add_call(Fq a, Fq b, Fq c, Fq d) { return Fq::mul2_add(a, b, c, d); }
+__device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return Fq::mul(a, b); }
+__device__ __noinline__ Fq fq_mul4_add_call(Fq a, Fq b, Fq c, Fq d, Fq e, Fq f, Fq g, Fq h) { return Fq::mul4_add(a, b, c, d, e, f, g, h); }
+
+struct PairLane {
+  uint32_t mask;  // the two lanes of this pair
+  bool hi;        // this lane holds c1
+  B2_D Fq partner(const Fq& a) const {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_xor_sync(mask, a.v[i], 1);
+    return r;
+  }
+  B2_D bool both(bool mine) const { return __shfl_xor_sync(mask, mine ? 1u : 0u, 1) != 0 && mine; }
+  B2_D Fq sel(const Fq& if_hi, const Fq& if_lo) const {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = hi ? if_hi.v[i] : if_lo.v[i];
+    return r;
+  }
+  // component of a * b; pa / pb = the partner's component of a / b
+  B2_D Fq mul(const Fq& a, const Fq& pa, const Fq& b, const Fq& pb) const {
+    // lo: a b + (-pa) pb      hi: a pb + pa b
+    return fq_mul2_add_call(a, sel(pb, b), sel(pa, Fq::neg(pa)), sel(b, pb));
+  }
+  B2_D Fq sqr(const Fq& a, const Fq& pa) const {
+    // lo: (a + pa)(a - pa)    hi: (2 a) pa
+    return fq_mul_call(sel(Fq::dbl(a), Fq::add(a, pa)), sel(pa, Fq::sub(a, pa)));
+  }
+  // component of a * b - c * d
+  B2_D Fq mul2_sub(const Fq& a, const Fq& pa, const Fq& b, const Fq& pb, const Fq& c, const Fq& pc, const Fq& d, const Fq& pd) const {
+    // lo: a b + (-pa) pb + (-c) d + pc pd      hi: pa b + a pb + (-pc) d + (-c) pd
+    const Fq nc = Fq::neg(c);
+    return fq_mul4_add_call(sel(pa, a), b, sel(a, Fq::neg(pa)), pb, sel(Fq::neg(pc), nc), d, sel(nc, pc), pd);
+  }
+  // two independent products (a b, c d) in one call
+  B2_D FqPair mul_x2(const Fq& a, const Fq& pa, const Fq& b, const Fq& pb, const Fq& c, const Fq& pc, const Fq& d, const Fq& pd) const {
+    return fq_mul2_add_x2_call(a, sel(pb, b), sel(pa, Fq::neg(pa)), sel(b, pb), c, sel(pd, d), sel(pc, Fq::neg(pc)), sel(d, pd));
+  }
+  // two independent squares (a^2, c^2) in one call
+  B2_D FqPair sqr_x2(const Fq& a, const Fq& pa, const Fq& c, const Fq& pc) const {
+    return fq_mul_x2_call(sel(Fq::dbl(a), Fq::add(a, pa)), sel(pa, Fq::sub(a, pa)), sel(Fq::dbl(c), Fq::add(c, pc)), sel(pc, Fq::sub(c, pc)));
+  }
+  B2_D Fq one() const { return hi ? Fq::zero() : Fq::one(); }
+};
+struct XYZZHalf { Fq x, y, zz, zzz; };  // one component of an XYZZ<Fq2>
+
+// acc = 2 * (x1, y1), affine input (mdbl-2008-s-1, a = 0)
+B2_D void pair_mdbl(const PairLane& L, XYZZHalf& acc, const Fq& x1, const Fq& y1) {
+  const Fq U = Fq::dbl(y1), pU = L.partner(U);
+  const Fq V = L.sqr(U, pU), pV = L.partner(V);
+  const Fq W = L.mul(U, pU, V, pV), pW = L.partner(W);
+  const Fq px1 = L.partner(x1), py1 = L.partner(y1);
+  const Fq S = L.mul(x1, px1, V, pV);
+  const Fq xx = L.sqr(x1, px1), M = Fq::add(Fq::dbl(xx), xx), pM = L.partner(M);
+  acc.x = Fq::sub(L.sqr(M, pM), Fq::dbl(S));
+  const Fq T = Fq::sub(S, acc.x), pT = L.partner(T);
+  acc.y = L.mul2_sub(M, pM, T, pT, W, pW, y1, py1);
+  acc.zz = V; acc.zzz = W;
+}
+// acc += (x2, y2)   (madd-2008-s; identity, doubling and cancellation handled; decisions are pair-uniform)
+B2_D void pair_add_mixed(const PairLane& L, XYZZHalf& acc, const Fq& x2, const Fq& y2) {
+  if (L.both(x2.is_zero() && y2.is_zero())) return;
+  if (L.both(acc.zz.is_zero())) { acc.x = x2; acc.y = y2; acc.zz = L.one(); acc.zzz = L.one(); return; }
+  const Fq pzz = L.partner(acc.zz), pzzz = L.partner(acc.zzz);
+  const FqPair us = L.mul_x2(x2, L.partner(x2), acc.zz, pzz, y2, L.partner(y2), acc.zzz, pzzz);  // U2 | S2
+  const Fq P = Fq::sub(us.r0, acc.x), R = Fq::sub(us.r1, acc.y);
+  if (L.both(P.is_zero())) {
+    if (L.both(R.is_zero())) pair_mdbl(L, acc, x2, y2);
+    else { acc.x = Fq::zero(); acc.y = Fq::zero(); acc.zz = Fq::zero(); acc.zzz = Fq::zero(); }
+    return;
+  }
+  const Fq pP = L.partner(P), pR = L.partner(R);
+  const FqPair sq = L.sqr_x2(P, pP, R, pR);  // PP | R^2
+  const Fq PP = sq.r0, pPP = L.partner(PP);
+  const FqPair pq = L.mul_x2(P, pP, PP, pPP, acc.x, L.partner(acc.x), PP, pPP);  // PPP | Q
+  const Fq PPP = pq.r0, pPPP = L.partner(PPP), Q = pq.r1;
+  const Fq x3 = Fq::sub(Fq::sub(sq.r1, PPP), Fq::dbl(Q));
+  const Fq T = Fq::sub(Q, x3), pT = L.partner(T);
+  const Fq y3 = L.mul2_sub(R, pR, T, pT, acc.y, L.partner(acc.y), PPP, pPPP);
+  const FqPair zz = L.mul_x2(acc.zz, pzz, PP, pPP, acc.zzz, pzzz, PPP, pPPP);  // ZZ3 | ZZZ3
+  acc.x = x3; acc.y = y3; acc.zz = zz.r0; acc.zzz = zz.r1;
+}
+
+// one thread PAIR per slice of kSegLen sorted entries; blockDim.x threads = blockDim.x / 2 slices
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_accumulate_g2_pair(const void* __restrict__ points, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ offsets,
+                                                                const uint32_t* __restrict__ run_off, uint32_t G, uint32_t kSegLen, void* __restrict__ partials,
+                                                                uint32_t* __restrict__ run_bucket) {
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = gt >> 1;
+  PairLane L;
+  L.hi = (threadIdx.x & 1) != 0;
+  L.mask = 3u << (threadIdx.x & 30);
+  const uint32_t M = __ldg(offsets + G);
+  const uint64_t e0_64 = (uint64_t)t * kSegLen;
+  if (e0_64 >= M) return;  // pair-uniform
+  const uint32_t e0 = (uint32_t)e0_64;
+  const uint32_t e1 = (M - e0 > kSegLen) ? e0 + kSegLen : M;
+  uint32_t g;
+  {
+    uint32_t lo = 0, hi = G;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= e0) lo = mid; else hi = mid; }
+    g = lo;
+  }
+  const uint32_t off0 = __ldg(offsets + g);
+  uint32_t slot = t + (__ldg(run_off + g) - (off0 + kSegLen - 1) / kSegLen) + ((off0 % kSegLen) ? 1u : 0u);
+  uint32_t next = __ldg(offsets + g + 1);
+  // affine G2 point = x.c0 | x.c1 | y.c0 | y.c1 (4 x 32 B): this lane's components sit at words 0 + hi and 2 + hi
+  const uint32_t comp = L.hi ? 1u : 0u;
+  auto load_half = [&](uint32_t v, Fq& x, Fq& y) {
+    const size_t w = 4 * (size_t)(v & 0x7fffffffu) + comp;
+    x = load_fe_nc<Fq>(points, w);
+    y = load_fe_nc<Fq>(points, w + 2);
+  };
+  // XYZZ<Fq2> partial = 8 words: x.c0 x.c1 y.c0 y.c1 zz.c0 zz.c1 zzz.c0 zzz.c1
+  auto store_half = [&](uint32_t s, const XYZZHalf& a) {
+    const size_t w = 8 * (size_t)s + comp;
+    store_fe<Fq>(partials, w, a.x); store_fe<Fq>(partials, w + 2, a.y); store_fe<Fq>(partials, w + 4, a.zz); store_fe<Fq>(partials, w + 6, a.zzz);
+  };
+  XYZZHalf acc = {Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()};
+  uint32_t v = __ldg(idx + e0);
+  Fq px, py;
+  load_half(v, px, py);
+  for (uint32_t e = e0; e < e1; ++e) {
+    uint32_t vn = v; Fq nx = px, ny = py;
+    if (e + 1 < e1) { vn = __ldg(idx + e + 1); load_half(vn, nx, ny); }  // next gather in flight during the addition
+    if (e == next) {  // bucket boundary: close the run
+      store_half(slot, acc);
+      if (!L.hi) run_bucket[slot] = g;
+      ++slot;
+      acc = {Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()};
+      g = bucket_of(offsets, G, g + 1, e);
+      next = __ldg(offsets + g + 1);
+    }
+    if (v >> 31) py = Fq::neg(py);  // -(y0 + y1 u) = -y0 + (-y1) u: component-wise
+    pair_add_mixed(L, acc, px, py);
+    v = vn; px = nx; py = ny;
+  }
+  store_half(slot, acc);
+  if (!L.hi) run_bucket[slot] = g;
 }
 
 // ---- batched-affine pair summing ---------------------------------------------------------------------------
@@ -909,6 +1120,23 @@ B2_D void encode_point(uint8_t* out, const Affine<Fq2>& p, bool native) {
   store_be32(out, Fq::from_mont(p.x.c1)); store_be32(out + 32, Fq::from_mont(p.x.c0));
   store_be32(out + 64, Fq::from_mont(p.y.c1)); store_be32(out + 96, Fq::from_mont(p.y.c0));
 }
+// BLS12-381 G1: native = x | y Montgomery limbs (96 B); else the 48-byte compressed form (big-endian x; bit 7 of byte 0 =
+// compressed, bit 6 = infinity, bit 5 = y is the lexicographically larger root) followed by 48 zero bytes, so that the
+// [point][is_infinity] layout below keeps the slot size 2 * FieldBytes
+B2_D void encode_point(uint8_t* out, const Affine<Fp381>& p, bool native) {
+  if (native) { store_affine<Fp381>(out, 0, p); return; }
+  uint32_t* o = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+  for (int k = 0; k < 24; ++k) o[k] = 0;
+  if (p.is_inf()) { out[0] = 0xc0; return; }
+  const Fp381 x = Fp381::from_mont(p.x), y = Fp381::from_mont(p.y);
+  Fp381 half;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) half.v[i] = Fp381Cfg::half(i);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) o[k] = __byte_perm(x.v[11 - k], 0, 0x0123);
+  out[0] |= 0x80 | (Fp381::less(half, y) ? 0x20 : 0x00);
+}
 // d_out layout: [encoded point (64 or 128 B)] [uint32 is_infinity]
 template <class F>
 __global__ void msm_encode(const void* __restrict__ partials, size_t count, bool native, uint8_t* __restrict__ out) {
@@ -956,18 +1184,51 @@ static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
   if (ctx->profiling) cudaEventRecord(ctx->ev[k], st);
 }
 
+// ---- accumulation launch: G1 one thread per slice; G2 one lane PAIR per slice (msm_accumulate_g2_pair) unless the knob says otherwise
+static int g2_pair_knob() {
+  // experiment knob B200ZK_G2_PAIR=0: the one-thread-per-slice G2 kernel; 2 | 3 | 4: CTAs per SM the lane-pair kernel is
+  // compiled for (203 registers uncapped / 168 / 128)
+  static int k = -1;
+  if (k < 0) { const char* e = getenv("B200ZK_G2_PAIR"); k = (e && *e >= '0' && *e <= '4' && *e != '1') ? (*e - '0') : 3; }
+  return k;
+}
+template <class F> static size_t resident_slices(const b200zk_ctx* ctx) {
+  if (IsFq2<F>::value) { const int k = g2_pair_knob(); return (size_t)ctx->sm_count * (k ? 64u * (unsigned)k : 256u); }
+  return (size_t)ctx->sm_count * (sizeof(F) > 32 ? 256u : 512u);
+}
+template <class F>
+static int launch_accumulate(b200zk_ctx* ctx, cudaStream_t st, const void* pts, const uint32_t* idx, const uint32_t* offsets, const uint32_t* run_off, uint32_t G, uint32_t L,
+                             size_t slices, void* partials, uint32_t* run_bucket) {
+  const unsigned agrid = (unsigned)((slices + 127) / 128);
+  if constexpr (IsFq2<F>::value) {
+    const int k = g2_pair_knob();
+    const unsigned pgrid = (unsigned)((2 * slices + 127) / 128);
+    if (k == 2) B2_LAUNCH(ctx, msm_accumulate_g2_pair<2>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
+    else if (k == 3) B2_LAUNCH(ctx, msm_accumulate_g2_pair<3>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
+    else if (k == 4) B2_LAUNCH(ctx, msm_accumulate_g2_pair<4>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
+    else B2_LAUNCH(ctx, (msm_accumulate<F, false, 1>), agrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
+  } else {
+    B2_LAUNCH(ctx, (msm_accumulate<F, false>), agrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
+  }
+  return B200ZK_OK;
+}
+
 // two-level sort of the (window,bucket) entries of n scalars: hist[G], offsets[G+1] and idx[M] come out exactly as the
-// legacy msm_hist / scan / msm_scatter sequence leaves them.  val1: W*n u32 scratch, key1: W*n u16 scratch, ctab: 2*(C*NC+1) u32.
+// legacy msm_hist / scan / msm_scatter sequence leaves them.  ent1: W*n 8-byte scratch (value | fine key), ctab: 2*(C*NC+1) u32.
 static int legacy_sort_knob() {
   static int knob = -1;  // experiment knob B200ZK_SORT=legacy: the r1 sort (one global atomic per entry and phase)
   if (knob < 0) { const char* e = getenv("B200ZK_SORT"); knob = (e && !strcmp(e, "legacy")) ? 1 : 0; }
   return knob;
 }
 static int run_two_level_sort(b200zk_ctx* ctx, const void* d_scalars, size_t n, uint32_t flags, const MsmPlan& pl, const SortPlan& sp, uint32_t* hist, uint32_t* offsets,
-                              uint32_t* tsum, uint32_t* val1, uint16_t* key1, uint32_t* ctab, uint32_t* idx, cudaStream_t st, bool mark) {
+                              uint32_t* tsum, uint2* ent1, uint32_t* ctab, uint32_t* idx, cudaStream_t st, bool mark) {
   const size_t Gc = (size_t)sp.C * sp.NC, tilesC = (Gc + kScanTile - 1) / kScanTile;
   uint32_t *cnt = ctab, *base = ctab + Gc + 1;
-  if (!ctx->attr_sort) { B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortCoarseSmem))); ctx->attr_sort = true; }
+  if (!ctx->attr_sort) {
+    B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortCoarseSmem)));
+    B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortFineSmem)));
+    ctx->attr_sort = true;
+  }
   B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, (Gc + 1) * 4, st));
   B2_LAUNCH(ctx, msm_sort_count, sp.NC * kSortCountSub, kHistTile, 0, st, d_scalars, n, flags, pl, sp, cnt);
   if (mark) phase_mark(ctx, 1, st);
@@ -975,46 +1236,40 @@ static int run_two_level_sort(b200zk_ctx* ctx, const void* d_scalars, size_t n, 
   B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tilesC);
   B2_LAUNCH(ctx, scan_apply, (unsigned)tilesC, kScanThreads, 0, st, (const uint32_t*)cnt, (const uint32_t*)nullptr, Gc, 0u, 0u, (const uint32_t*)tsum, base, (uint32_t*)nullptr);
   if (mark) phase_mark(ctx, 2, st);
-  B2_LAUNCH(ctx, msm_sort_coarse, sp.NC, kSortTile, sizeof(SortCoarseSmem), st, d_scalars, n, flags, pl, sp, (const uint32_t*)base, val1, key1);
-  B2_LAUNCH(ctx, msm_sort_fine, sp.C, 1024, 0, st, (const uint32_t*)val1, (const uint16_t*)key1, sp, (const uint32_t*)base, hist, offsets, idx);
+  B2_LAUNCH(ctx, msm_sort_coarse, sp.NC, kSortTile, sizeof(SortCoarseSmem), st, d_scalars, n, flags, pl, sp, (const uint32_t*)base, ent1);
+  B2_LAUNCH(ctx, msm_sort_fine, sp.C, 1024, sizeof(SortFineSmem), st, (const uint2*)ent1, sp, (const uint32_t*)base, hist, offsets, idx);
   return B200ZK_OK;
 }
 
 // ---- chunk-pipelined schedule --------------------------------------------------------------------------------
-// The sort (histogram / scan / scatter: L2-atomic and latency bound, the multiplier pipe idle) and the bucket
-// accumulation (multiplier-pipe bound, memory system idle) use disjoint resources, so for large n the points are
-// cut into chunks and chunk k+1 is sorted on a second, high-priority stream WHILE chunk k is accumulated; with
-// host scalars the chunk's upload rides on the sort stream too.  Each chunk's bucket totals are folded into a dense
-// totals array, which is reduced once at the end.
+// Host scalars arrive over PCIe (512 MiB at 2^24: ~10 ms, a quarter of the MSM).  The points are cut into K chunks;
+// chunk k's scalars are uploaded on a second stream while earlier chunks are being sorted and accumulated, so that only
+// the FIRST chunk's upload is exposed.  r1 also ran the sort of chunk k+1 concurrently with the accumulation of chunk k
+// (second stream, a shared-memory reservation to keep room on the SMs); with the r2 two-level sort -- whose CTAs want a
+// whole SM -- all kernels run on ONE stream in the order sort(0), accumulate(0), sort(1), ...: every kernel has the
+// machine to itself and the copy engine works underneath, one chunk ahead.  Each chunk's bucket totals are folded into a dense totals array, which is reduced once at the end.
 template <class F>
 static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, const void* h_scalars, size_t n, uint32_t flags,
                              cudaStream_t st, void* d_partial, const MsmPlan& pl, uint32_t K) {
   const size_t G = (size_t)pl.Wr * pl.B;
   const size_t tiles = (G + kScanTile - 1) / kScanTile;
   const size_t xy = 4 * FieldBytes<F>::value, pt = 2 * FieldBytes<F>::value;
-  size_t chunk = ((n + K - 1) / K + 255) & ~(size_t)255;
+  size_t chunk = ((n + K - 1) / K + 1023) & ~(size_t)1023;
   const size_t Mk_max = chunk * pl.W;
-  const size_t resident = (size_t)ctx->sm_count * (sizeof(F) > 32 ? 256 : 512);
+  const size_t resident = resident_slices<F>(ctx);
   const uint32_t L = pick_slice_len(Mk_max, resident);
   const size_t S_max = Mk_max / L + 1 + G;
   const size_t slices = (Mk_max + L - 1) / L;
+  SortPlan sp0;
+  const bool two_level = !legacy_sort_knob() && make_sort_plan(chunk, pl, ctx->sm_count, &sp0);
+  const size_t Gc = (size_t)kSortMaxBins * (size_t)ctx->sm_count;  // upper bound of C * NC for any chunk
   for (int sl = 0; sl < 2; ++sl) {
     SortSlot& s = ctx->slot[sl];
     B2_TRY(ensure(ctx, s.hist, G * 4)); B2_TRY(ensure(ctx, s.offsets, (G + 1) * 4)); B2_TRY(ensure(ctx, s.cursor, G * 4));
-    B2_TRY(ensure(ctx, s.run_off, (G + 1) * 4)); B2_TRY(ensure(ctx, s.tsum, tiles * 4));
+    B2_TRY(ensure(ctx, s.run_off, (G + 1) * 4));
+    B2_TRY(ensure(ctx, s.tsum, std::max(tiles, (Gc + kScanTile - 1) / kScanTile) * 4));
     B2_TRY(ensure(ctx, s.digits, Mk_max * 4)); B2_TRY(ensure(ctx, s.idx, Mk_max * 4));
-  }
-  // the two-level sort is planned for the chunk size (the last chunk may be shorter: re-planned per chunk below)
-  SortPlan sp0;
-  const bool two_level = !legacy_sort_knob() && make_sort_plan(chunk, pl, ctx->sm_count, &sp0);
-  if (two_level) {
-    const size_t Gc = (size_t)kSortMaxBins * (size_t)ctx->sm_count;  // upper bound of C * NC for any chunk
-    for (int sl = 0; sl < 2; ++sl) {
-      SortSlot& s = ctx->slot[sl];
-      B2_TRY(ensure(ctx, s.key, Mk_max * 2));
-      B2_TRY(ensure(ctx, s.ctab, 2 * (Gc + 1) * 4));
-      B2_TRY(ensure(ctx, s.tsum, std::max(tiles, (Gc + kScanTile - 1) / kScanTile) * 4));
-    }
+    if (two_level) { B2_TRY(ensure(ctx, s.key, Mk_max * 8)); B2_TRY(ensure(ctx, s.ctab, 2 * (Gc + 1) * 4)); }
   }
   B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));
   B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
@@ -1023,64 +1278,64 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
   B2_TRY(ensure(ctx, ctx->ws_chunkV, (size_t)pl.Wr * pl.T * xy));
   if (h_scalars) B2_TRY(ensure(ctx, ctx->ws_scalars, n * 32 + 32));
   const uint8_t* dsc = (const uint8_t*)(h_scalars ? ctx->ws_scalars.p : d_scalars);
-  cudaStream_t ss = ctx->stream_sort;
-  // Leave room on every SM for the sort kernels of the next chunk: the accumulation alone fills the register file
-  // (4 CTAs x 128 threads x 128 registers), so it is launched with a dynamic shared-memory reservation that caps it
-  // at 3 CTAs per SM; the high-priority sort stream's CTAs slot into the freed quarter.
-  static int acc_smem = -1;
-  if (acc_smem < 0) {
-    const char* e = getenv("B200ZK_MSM_ACC_SMEM_KB");
-    acc_smem = e ? atoi(e) * 1024 : 60 * 1024;  // 60 KiB -> 3 CTAs/SM (measured best of 0/60/76/100)
-    if (acc_smem > 48 * 1024) B2_CUDA(ctx, cudaFuncSetAttribute((msm_accumulate<F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, acc_smem));
+  cudaStream_t cs = ctx->stream_sort;  // the copy stream: uploads only
+  const uint32_t chunks = (uint32_t)((n + chunk - 1) / chunk);
+  // uploads: all issued up front on the copy stream (they serialise on the one H2D engine in chunk order); the staging
+  // buffer may still be read by the previous call's kernels on `st`, so the copy stream first waits for `st`
+  if (h_scalars) {
+    B2_CUDA(ctx, cudaEventRecord(ctx->ev_in, st));
+    B2_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_in, 0));
+    if (chunks > kMaxPipelineChunks) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: too many pipeline chunks");
+    for (uint32_t k = 0; k < chunks; ++k) {
+      const size_t lo = (size_t)k * chunk, nk = n - lo < chunk ? n - lo : chunk;
+      B2_CUDA(ctx, cudaMemcpyAsync((void*)(dsc + lo * 32), (const uint8_t*)h_scalars + lo * 32, nk * 32, cudaMemcpyHostToDevice, cs));
+      B2_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], cs));
+    }
   }
-  const size_t acc_dyn = (K > 1 && sizeof(F) == 32) ? (size_t)acc_smem : 0;
-  B2_CUDA(ctx, cudaEventRecord(ctx->ev_in, st));
-  B2_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_in, 0));
-  uint32_t k = 0;
-  for (size_t lo = 0; lo < n; lo += chunk, ++k) {
-    const size_t nk = n - lo < chunk ? n - lo : chunk;
+  auto sort_chunk = [&](uint32_t k) -> int {
+    const size_t lo = (size_t)k * chunk, nk = n - lo < chunk ? n - lo : chunk;
     SortSlot& s = ctx->slot[k & 1];
     uint32_t *hist = (uint32_t*)s.hist.p, *offsets = (uint32_t*)s.offsets.p, *cursor = (uint32_t*)s.cursor.p, *run_off = (uint32_t*)s.run_off.p,
              *tsum = (uint32_t*)s.tsum.p, *digits = (uint32_t*)s.digits.p, *idx = (uint32_t*)s.idx.p;
-    // ---- sort stream
-    if (k >= 2) B2_CUDA(ctx, cudaStreamWaitEvent(ss, s.released, 0));
-    if (h_scalars) B2_CUDA(ctx, cudaMemcpyAsync((void*)(dsc + lo * 32), (const uint8_t*)h_scalars + lo * 32, nk * 32, cudaMemcpyHostToDevice, ss));
+    if (h_scalars) B2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_up[k], 0));
     SortPlan sp;
     const bool tl = two_level && make_sort_plan(nk, pl, ctx->sm_count, &sp);
     if (tl) {
-      B2_TRY(run_two_level_sort(ctx, (const void*)(dsc + lo * 32), nk, flags, pl, sp, hist, offsets, tsum, digits, (uint16_t*)s.key.p, (uint32_t*)s.ctab.p, idx, ss, false));
+      B2_TRY(run_two_level_sort(ctx, (const void*)(dsc + lo * 32), nk, flags, pl, sp, hist, offsets, tsum, (uint2*)s.key.p, (uint32_t*)s.ctab.p, idx, st, false));
     } else {
-      B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, ss));
+      B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
       const unsigned sgrid = (unsigned)std::min<size_t>((nk + 255) / 256, (size_t)ctx->sm_count * 8);
-      B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, ss, (const void*)(dsc + lo * 32), nk, flags, pl, hist, digits);
-      B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
-      B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
-      B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
-    }
-    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)offsets, G, L, 0u, tsum);
-    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, ss, tsum, tiles);
-    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, ss, hist, (const uint32_t*)offsets, G, L, 0u, tsum, run_off, (uint32_t*)nullptr);
-    if (!tl) {
+      B2_LAUNCH(ctx, msm_hist, sgrid, 256, 0, st, (const void*)(dsc + lo * 32), nk, flags, pl, hist, digits);
+      B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
+      B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+      B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum, offsets, cursor);
       const unsigned wgrid = (unsigned)std::min<size_t>((nk * (size_t)pl.W + 255) / 256, (size_t)ctx->sm_count * 32);
-      B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, ss, (const uint32_t*)digits, nk, pl, cursor, idx);
+      B2_LAUNCH(ctx, msm_scatter, wgrid, 256, 0, st, (const uint32_t*)digits, nk, pl, cursor, idx);
     }
-    B2_CUDA(ctx, cudaEventRecord(s.sorted, ss));
-    // ---- accumulate stream (the caller's)
-    B2_CUDA(ctx, cudaStreamWaitEvent(st, s.sorted, 0));
+    B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)offsets, G, L, 0u, tsum);
+    B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tiles);
+    B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, (const uint32_t*)offsets, G, L, 0u, tsum, run_off, (uint32_t*)nullptr);
+    return B200ZK_OK;
+  };
+  for (uint32_t k = 0; k < chunks; ++k) {
+    const size_t lo = (size_t)k * chunk, nk = n - lo < chunk ? n - lo : chunk;
+    // sort(k) waits for upload k only: with the kernels serialised there is nothing to gain from sorting ahead (measured:
+    // sort(k+1) before accumulate(k) stalls the stream on upload k+1 -- 42.0 ms at 2^24 against the order below)
+    B2_TRY(sort_chunk(k));
+    SortSlot& s = ctx->slot[k & 1];
     const void* pts = (const uint8_t*)d_points + lo * pt;
-    B2_LAUNCH(ctx, (msm_accumulate<F, false>), (unsigned)((slices + 127) / 128), 128, acc_dyn, st, pts, (const uint32_t*)idx, (const uint32_t*)offsets, (const uint32_t*)run_off,
-              (uint32_t)G, L, ctx->ws_buckets.p, (uint32_t*)ctx->ws_segbucket.p);
+    B2_TRY(launch_accumulate<F>(ctx, st, pts, (const uint32_t*)s.idx.p, (const uint32_t*)s.offsets.p, (const uint32_t*)s.run_off.p, (uint32_t)G, L, slices, ctx->ws_buckets.p,
+                                (uint32_t*)ctx->ws_segbucket.p));
     {
       size_t worst_entries = (pl.merged ? nk * (size_t)pl.W : nk) + 1;
       size_t worst = (worst_entries + L - 1) / L + 1;
       for (size_t stride = 1; stride < worst; stride *= kTreeRadix)
-        B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, (const uint32_t*)run_off, (const uint32_t*)ctx->ws_segbucket.p, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
+        B2_LAUNCH(ctx, partial_tree<F>, (unsigned)((S_max + 127) / 128), 128, 0, st, (const uint32_t*)s.run_off.p, (const uint32_t*)ctx->ws_segbucket.p, (uint32_t)G, (uint32_t)stride, ctx->ws_buckets.p);
     }
-    B2_LAUNCH(ctx, bucket_merge<F>, (unsigned)((G + 127) / 128), 128, 0, st, (const void*)ctx->ws_buckets.p, (const uint32_t*)run_off, (uint32_t)G, k == 0 ? 1 : 0, ctx->ws_totals.p);
-    B2_CUDA(ctx, cudaEventRecord(s.released, st));
+    B2_LAUNCH(ctx, bucket_merge<F>, (unsigned)((G + 127) / 128), 128, 0, st, (const void*)ctx->ws_buckets.p, (const uint32_t*)s.run_off.p, (uint32_t)G, k == 0 ? 1 : 0, ctx->ws_totals.p);
   }
-  const size_t chunks = (size_t)pl.Wr * pl.T;
-  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, (const void*)ctx->ws_totals.p, (const uint32_t*)nullptr, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  const size_t nchunks = (size_t)pl.Wr * pl.T;
+  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((nchunks + 127) / 128), 128, 0, st, (const void*)ctx->ws_totals.p, (const uint32_t*)nullptr, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
   uint32_t chunk_log2 = 0;
   while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
   if (pl.T >= 64) {
@@ -1102,7 +1357,7 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
 template <class F>
 static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars, size_t n, uint32_t flags, cudaStream_t st, void* d_partial,
                    uint32_t table_c, size_t table_stride, const void* h_scalars, int sort_mode) {
-  NvtxRange nvtx_msm(sizeof(F) > 32 ? "b200zk:g2_msm" : "b200zk:g1_msm");
+  NvtxRange nvtx_msm(IsFq2<F>::value ? "b200zk:g2_msm" : (sizeof(F) > 32 ? "b200zk:bls12_381_g1_msm" : "b200zk:g1_msm"));
   // sort_mode (b200zk_msm_multi_resident_device): 0 = ordinary call; 1 = one-shot schedule, the digit sort stays in
   // the workspaces; 2 = the sort of the previous call (same scalars, same plan) is reused: only the point-dependent
   // half of the MSM runs (run scan, accumulation, bucket reduction)
@@ -1113,7 +1368,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   if (n >= ((size_t)1 << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
   // 128-bit loads and the bulk copies of the scalar tiles need 16-byte aligned device buffers
   if (((uintptr_t)d_points & 15) || ((uintptr_t)d_scalars & 15)) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: device buffers must be 16-byte aligned");
-  MsmPlan pl = make_plan(n, table_c ? table_c : ctx->msm_window);
+  MsmPlan pl = make_plan(n, table_c ? table_c : ctx->msm_window, ScalarBits<F>::value);
   if (table_c) {
     pl.merged = 1; pl.Wr = 1; pl.table_stride = (uint32_t)table_stride;
     if ((unsigned long long)table_stride * pl.W >= (1ull << 31)) return fail(ctx, B200ZK_ERR_UNSUPPORTED, "msm: precomputed table too large for 31-bit indices");
@@ -1124,6 +1379,8 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
     // measured on B200 (profiles/r1_probe.md): with scalars already in HBM one shot is as fast as any chunking
     // (40.9 ms vs 40.0-42 ms at 2^24: the accumulation fills the SMs, so the next chunk's sort barely overlaps);
     // with HOST scalars 4 chunks hide most of the 512 MiB upload (50.5 -> 41.9 ms)
+    // chunks of the host-scalar pipeline: 4 measured best at 2^24 (tools/e2e_sweep.py, profiles/r2_e2e_sweep.jsonl: 46.5 / 42.0 /
+    // 40.6 / 40.9 / 41.3 / 43.4 ms for 1 / 2 / 4 / 6 / 8 / 12 chunks against 36.8 ms with resident scalars)
     uint32_t K = ctx->msm_chunks ? ctx->msm_chunks : ((h_scalars && n >= ((size_t)1 << 22)) ? 4u : 1u);
     if (K > 64) K = 64;
     if (sort_mode == 0 && (K > 1 || h_scalars) && !ctx->profiling && ctx->msm_pair_rounds <= 0 && n >= 4096)
@@ -1153,7 +1410,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   if (rounds > 4) rounds = 4;
   if (rounds && M_max >= ((size_t)1 << 31)) rounds = 0;
   if (sort_mode) rounds = 0;
-  const uint32_t kSegLen = pick_slice_len(M_max >> rounds, (size_t)ctx->sm_count * (sizeof(F) > 32 ? 256 : 512));
+  const uint32_t kSegLen = pick_slice_len(M_max >> rounds, resident_slices<F>(ctx));
   const size_t S_max = (M_max >> rounds) / kSegLen + 1 + G;  // upper bound on the number of runs
   const size_t slices = ((M_max >> rounds) + G + kSegLen - 1) / kSegLen;
   if (rounds) {
@@ -1179,7 +1436,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   SortPlan sp;
   const bool two_level = !legacy_sort_knob() && make_sort_plan(n, pl, ctx->sm_count, &sp);
   if (two_level) {
-    B2_TRY(ensure(ctx, ctx->ws_key, M_max * 2));
+    B2_TRY(ensure(ctx, ctx->ws_key, M_max * 8));
     B2_TRY(ensure(ctx, ctx->ws_ctab, (2 * ((size_t)sp.C * sp.NC + 1)) * 4));
     B2_TRY(ensure(ctx, ctx->ws_blocksums, (std::max(tiles, ((size_t)sp.C * sp.NC + kScanTile - 1) / kScanTile)) * 4));
     tsum = (uint32_t*)ctx->ws_blocksums.p;
@@ -1187,7 +1444,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   phase_mark(ctx, 0, st);
   nvtxRangePushA("b200zk:msm_sort");
   if (sort_mode != 2 && two_level) {
-    B2_TRY(run_two_level_sort(ctx, d_scalars, n, flags, pl, sp, hist, offsets, tsum, (uint32_t*)ctx->ws_digits.p, (uint16_t*)ctx->ws_key.p, (uint32_t*)ctx->ws_ctab.p, idx, st, true));
+    B2_TRY(run_two_level_sort(ctx, d_scalars, n, flags, pl, sp, hist, offsets, tsum, (uint2*)ctx->ws_key.p, (uint32_t*)ctx->ws_ctab.p, idx, st, true));
   } else if (sort_mode != 2) {
     B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
     const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
@@ -1230,19 +1487,7 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   B2_LAUNCH(ctx, scan_apply, (unsigned)tiles, kScanThreads, 0, st, hist, cur_off, G, kSegLen, 0u, tsum, seg_off, (uint32_t*)nullptr);
   if (rounds) B2_LAUNCH(ctx, (msm_accumulate<F, true>), (unsigned)((slices + 127) / 128), 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
   else {
-    // G2: the uncapped build takes 255 registers (2 CTAs = 8 warps per SM); MINB caps it at 168 / 128 for 3 / 4 CTAs.
-    // Experiment knob B200ZK_G2_MINB=1|2|3|4 (Fq2 only; measured in profiles/r1h_g2_occupancy.md)
-    static int g2_minb = 0;
-    if (!g2_minb) { const char* e = getenv("B200ZK_G2_MINB"); g2_minb = (e && *e >= '1' && *e <= '4') ? (*e - '0') : kG2MinBlocks; }
-    const unsigned agrid = (unsigned)((slices + 127) / 128);
-    if constexpr (sizeof(F) > 32) {
-      if (g2_minb == 4) B2_LAUNCH(ctx, (msm_accumulate<F, false, 4>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
-      else if (g2_minb == 3) B2_LAUNCH(ctx, (msm_accumulate<F, false, 3>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
-      else if (g2_minb == 2) B2_LAUNCH(ctx, (msm_accumulate<F, false, 2>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
-      else B2_LAUNCH(ctx, (msm_accumulate<F, false, 1>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
-    } else {
-      B2_LAUNCH(ctx, (msm_accumulate<F, false>), agrid, 128, 0, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, ctx->ws_buckets.p, seg_bucket);
-    }
+    B2_TRY(launch_accumulate<F>(ctx, st, cur_pts, (const uint32_t*)idx, cur_off, (const uint32_t*)seg_off, (uint32_t)G, kSegLen, slices, ctx->ws_buckets.p, seg_bucket));
   }
   {
     // worst case every point of a window lands in one bucket: ceil(entries / kSegLen) + 1 runs to fold
@@ -1297,7 +1542,7 @@ __global__ void __launch_bounds__(128) precompute_windows(const void* __restrict
 }
 template <class F>
 static int precompute_host(b200zk_ctx* ctx, const void* d_bases, size_t n, uint32_t c, void* d_table, cudaStream_t st) {
-  const uint32_t W = (255 + c - 1) / c;
+  const uint32_t W = (ScalarBits<F>::value + c - 1) / c;
   if (n) B2_LAUNCH(ctx, precompute_windows<F>, (unsigned)((n + 127) / 128), 128, 0, st, d_bases, n, c, W, d_table);
   return B200ZK_OK;
 }
@@ -1306,6 +1551,9 @@ int msm_precompute_g2(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void
 
 int msm_run_g1(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs, int sort_mode) { return msm_run<Fq>(ctx, p, s, n, f, st, out, tc, ts, hs, sort_mode); }
 int msm_run_g2(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs, int sort_mode) { return msm_run<Fq2>(ctx, p, s, n, f, st, out, tc, ts, hs, sort_mode); }
+int msm_run_bls(b200zk_ctx* ctx, const void* p, const void* s, size_t n, uint32_t f, cudaStream_t st, void* out, uint32_t tc, size_t ts, const void* hs, int sort_mode) { return msm_run<Fp381>(ctx, p, s, n, f | B200ZK_SCALARS_RAW, st, out, tc, ts, hs, sort_mode); }
+int msm_precompute_bls(b200zk_ctx* ctx, const void* b, size_t n, uint32_t c, void* t, cudaStream_t st) { return precompute_host<Fp381>(ctx, b, n, c, t, st); }
+int msm_encode_bls(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fp381>(ctx, p, c, f, st, out); }
 int msm_encode_g1(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq>(ctx, p, c, f, st, out); }
 int msm_encode_g2(b200zk_ctx* ctx, const void* p, size_t c, uint32_t f, cudaStream_t st, void* out) { return msm_encode_host<Fq2>(ctx, p, c, f, st, out); }
 

@@ -375,18 +375,18 @@ static int launch_pass(b200zk_ctx* ctx, const PassArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)items * 32;
   const unsigned grid = 1u << (a.log_n - a.s - a.t);
   if (items >= 4096) {
-    static bool attr512 = false;
-    if (!attr512) { B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 17)); attr512 = true; }
+    // the opt-in to > 48 KiB of dynamic shared memory is a per-device function attribute: remembered per context
+    if (!ctx->attr_ntt512) { B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 17)); ctx->attr_ntt512 = true; }
     B2_LAUNCH(ctx, (ntt_pass<512, 1>), grid, 512, smem, st, a);
   } else {
     // 64 KiB tiles: three CTAs fit an SM's shared memory; MINB = 3 caps registers at 85 so that they also fit
     // its register file (experiment knob B200ZK_NTT_MINB=2 keeps the uncapped 100-register build)
-    static int minb = 0;
-    if (!minb) {
-      const char* e = getenv("B200ZK_NTT_MINB");
-      minb = (e && *e == '2') ? 2 : 3;
+    static int minb = 0;  // the knob only (an environment variable is process-wide by nature)
+    if (!minb) { const char* e = getenv("B200ZK_NTT_MINB"); minb = (e && *e == '2') ? 2 : 3; }
+    if (!ctx->attr_ntt256) {
       B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<256, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16));
       B2_CUDA(ctx, cudaFuncSetAttribute((ntt_pass<256, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << 16));
+      ctx->attr_ntt256 = true;
     }
     if (minb == 2) B2_LAUNCH(ctx, (ntt_pass<256, 2>), grid, 256, smem, st, a);
     else B2_LAUNCH(ctx, (ntt_pass<256, 3>), grid, 256, smem, st, a);

@@ -80,7 +80,9 @@ enum {
   B200ZK_NTT_CANONICAL = 1u << 6,   /* NTT data are canonical little-endian limbs (converted on device) */
   B200ZK_NTT_BE = 1u << 7,          /* NTT data are 32-byte big-endian canonical values */
   B200ZK_G16_INPUTS_DEVICE = 1u << 8, /* b200zk_groth16_commit*: witness and evaluation buffers are DEVICE pointers (used in place) */
-  B200ZK_G16_H_COEFFS = 1u << 9     /* b200zk_groth16_commit*: a_evals already holds the quotient's coefficients (Montgomery); skip the NTTs */
+  B200ZK_G16_H_COEFFS = 1u << 9,    /* b200zk_groth16_commit*: a_evals already holds the quotient's coefficients (Montgomery); skip the NTTs */
+  B200ZK_SCALARS_RAW = 1u << 10,    /* scalars are plain 256-bit integers < 2^255, NOT reduced mod the BN254 group order (BLS12-381 calls) */
+  B200ZK_POINTS_COMPRESSED = 1u << 11 /* BLS12-381 G1 points in the 48-byte compressed ZCash / IETF format (the trusted setup's form) */
 };
 
 /* ---- lifecycle (ProverBackend::new / process-global OnceLock, cf. sp1.rs:30,93-95) ------------------- */
@@ -261,6 +263,25 @@ int b200zk_groth16_commit_partial(b200zk_ctx* ctx, const b200zk_groth16_pk* pk, 
                                   void* b_evals, void* c_evals, uint32_t flags, void* stream, void* d_partials768);
 int b200zk_groth16_fold(b200zk_ctx* ctx, const void* d_partials, size_t count, void* stream, uint8_t proof[256],
                         uint8_t b_g1[64]);
+
+/* ---- BLS12-381 G1 / EIP-4844 blob commitments -------------------------------------
+ * The L2 committer's "commit" step: /root/reference/crates/common/crypto/kzg.rs:259-272 (blob_to_kzg_commitment_and_proof ->
+ * c_kzg blob_to_kzg_commitment), /root/reference/crates/common/types/blobs_bundle.rs:90-118, crates/l2/sequencer/
+ * l1_committer.rs:1488-1521.  The same Pippenger kernels, instantiated over the 381-bit base field (12 x 32-bit limbs).
+ * Points: 48-byte compressed (B200ZK_POINTS_COMPRESSED; bit 7 of byte 0 = compressed, bit 6 = infinity, bit 5 = the larger
+ * y) -- the form the trusted setup ships in -- or 96-byte uncompressed big-endian x | y.  Statuses: 2 = a coordinate or a
+ * scalar out of its field, 3 = not a curve point / malformed flag bits.  The subgroup check is the trusted setup's
+ * business (c-kzg validates it when loading), not repeated here.  The handle works with b200zk_bases_precompute /
+ * b200zk_bases_free like any other.  Scalars: 32-byte integers < the BLS12-381 group order r, little-endian limbs or
+ * big-endian with B200ZK_SCALARS_BE (then checked against r); result: 48 bytes compressed. */
+int b200zk_bls12_381_g1_bases_upload(b200zk_ctx* ctx, const void* points, size_t n, uint32_t flags, uint64_t* handle);
+int b200zk_bls12_381_g1_msm_resident(b200zk_ctx* ctx, uint64_t handle, const void* scalars, size_t n, uint32_t flags,
+                                     uint8_t out[48]);
+/* blob_to_kzg_commitment for n_blobs blobs: blob = 4096 x 32-byte big-endian field elements (each < r, else status 2);
+ * setup_handle = the 4096 Lagrange-form G1 points of the trusted setup (g1_lagrange_brp order, as c-kzg holds them);
+ * commitments: n_blobs x 48 bytes */
+int b200zk_kzg_blob_to_commitment(b200zk_ctx* ctx, uint64_t setup_handle, const uint8_t* blobs, size_t n_blobs,
+                                  uint8_t* commitments);
 
 /* ---- batched EIP-196 / EIP-197 precompile arithmetic ------------------------------
  * The three BN254 calls of the reference's `Crypto` trait, `count` independent items per call, HOST buffers:

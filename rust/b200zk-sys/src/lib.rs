@@ -39,6 +39,8 @@ pub const B200ZK_NTT_CANONICAL: u32 = 1 << 6;
 pub const B200ZK_NTT_BE: u32 = 1 << 7;
 pub const B200ZK_G16_INPUTS_DEVICE: u32 = 1 << 8;
 pub const B200ZK_G16_H_COEFFS: u32 = 1 << 9;
+pub const B200ZK_SCALARS_RAW: u32 = 1 << 10;
+pub const B200ZK_POINTS_COMPRESSED: u32 = 1 << 11;
 
 /// `struct b200zk_groth16_pk` (include/b200zk.h): columns 0..4 = A_g1, B_g1 (handle 0 = absent), B_g2, L_g1, H_g1.
 #[repr(C)]
@@ -113,6 +115,9 @@ unsafe extern "C" {
     pub fn b200zk_set_profiling(ctx: *mut b200zk_ctx, enabled: c_int) -> c_int;
 
     pub fn b200zk_msm_multi_resident_device(ctx: *mut b200zk_ctx, handles: *const u64, count: usize, d_scalars: *const c_void, n: usize, flags: u32, stream: *mut c_void, out: *mut u8, status: *mut c_int) -> c_int;
+    pub fn b200zk_bls12_381_g1_bases_upload(ctx: *mut b200zk_ctx, points: *const c_void, n: usize, flags: u32, handle: *mut u64) -> c_int;
+    pub fn b200zk_bls12_381_g1_msm_resident(ctx: *mut b200zk_ctx, handle: u64, scalars: *const c_void, n: usize, flags: u32, out: *mut u8) -> c_int;
+    pub fn b200zk_kzg_blob_to_commitment(ctx: *mut b200zk_ctx, setup_handle: u64, blobs: *const u8, n_blobs: usize, commitments: *mut u8) -> c_int;
     pub fn b200zk_bn254_g1_add_batch(ctx: *mut b200zk_ctx, a: *const u8, b: *const u8, count: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn b200zk_bn254_g1_mul_batch(ctx: *mut b200zk_ctx, points: *const u8, scalars: *const u8, count: usize, out: *mut u8, status: *mut u8) -> c_int;
     pub fn b200zk_bn254_pairing_check_batch(ctx: *mut b200zk_ctx, pairs: *const u8, pair_offsets: *const u32, count: usize, result: *mut u8, status: *mut u8) -> c_int;

@@ -262,3 +262,26 @@ def test_ntt_root_presets_in_the_library_are_the_published_generators():
     want = [sum(a[j] * pow(w, j * k, o.R) for j in range(n)) % o.R for k in range(n)]
     got = orc.array_to_ints(orc.fr_from_mont(orc.fr_ntt(orc.fr_to_mont(orc.ints_to_array(a)), log_n, 0, root_2_28=halo2)))
     assert got == want
+
+
+def test_bls12_381_oracle_constants():
+    """oracle/bls_ref.py against the public constants of the curve: generator on the curve and of order r, its compressed
+    form, the identity's form, the 4096-th root of unity, the Lagrange basis summing to one -- and the product's host-side
+    KZG bookkeeping (ethrex_b200/kzg.py) agreeing with it on the domain."""
+    import bls_ref as b
+    from ethrex_b200 import kzg
+    assert b.on_curve(b.G1) and b.mul(b.R, b.G1) is None
+    assert b.compress(b.G1) == b.G1_COMPRESSED and b.decompress(b.G1_COMPRESSED) == b.G1
+    assert b.compress(None) == bytes([0xC0]) + bytes(47) and b.decompress(b.compress(None)) is None
+    neg = (b.G1[0], b.P - b.G1[1])
+    assert b.compress(neg)[0] & 0x20 != b.compress(b.G1)[0] & 0x20 and b.decompress(b.compress(neg)) == neg
+    assert pow(b.ROOT_4096, 4096, b.R) == 1 and pow(b.ROOT_4096, 2048, b.R) == b.R - 1
+    assert kzg.BLS_MODULUS == b.R and kzg.roots_of_unity_brp()[1] == pow(b.ROOT_4096, 2048, b.R)  # brp(1) = 2048
+    lag = b.lagrange_setup_scalars(987654321, 16)
+    assert sum(lag) % b.R == 1
+    assert b.generator_multiples([5, 0, b.R - 1]) == [b.mul(5, b.G1), None, b.mul(b.R - 1, b.G1)]
+    # Fiat-Shamir challenge: domain | degree | blob | commitment, reduced mod r
+    blob, c = bytes(4096 * 32), b.compress(None)
+    import hashlib
+    want = int.from_bytes(hashlib.sha256(b"FSBLOBVERIFY_V1_" + (4096).to_bytes(16, "big") + blob + c).digest(), "big") % b.R
+    assert kzg.KzgSettings.compute_challenge(blob, c) == want
