@@ -673,15 +673,11 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const void* __restri
 // no local-memory traffic).  Inlined, one G2 mixed addition is ~3500 SASS instructions = 56 KB and the loop body does not
 // fit the instruction cache (ncu r2g: stall_no_instruction 1.2 per issue, the top stall); as calls the body is ~13 KB plus
 // ~13 KB of callees, the size of the G1 kernel's body.
-// A call is a scheduling barrier, so a callee that computes ONE product leaves the multiplier pipe with a single carry
-// chain per warp (measured: no faster than the inlined body).  The callees therefore compute the TWO independent products
-// the XYZZ formulas offer at every step (U2 | S2, PP | R^2, PPP | Q, ZZ3 | ZZZ3): two interleaved chains per warp, like
-// the G1 kernel.
-struct FqPair { Fq r0, r1; };
-__device__ __noinline__ FqPair fq_mul_x2_call(Fq a, Fq b, Fq c, Fq d) { return {Fq::mul(a, b), Fq::mul(c, d)}; }
-__device__ __noinline__ FqPair fq_mul2_add_x2_call(Fq a, Fq b, Fq c, Fq d, Fq e, Fq f, Fq g, Fq h) { return {Fq::mul2_add(a, b, c, d), Fq::mul2_add(e, f, g, h)}; }
-__device__ __noinline__ Fq fq_mul2_add_call(Fq a, Fq b, Fq c, Fq d) { return Fq::mul2_add(a, b, c, d); }
+// One product per call: callees that compute the two independent products the formulas offer at every step (U2 | S2,
+// PP | R^2, PPP | Q, ZZ3 | ZZZ3) were measured too and lose (111-115 ms against 106 ms at 2^24: marshalling 64 argument
+// registers per call costs more than the second carry chain per warp gains; profiles/r2_g2_pair*.jsonl).
 __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return Fq::mul(a, b); }
+__device__ __noinline__ Fq fq_mul2_add_call(Fq a, Fq b, Fq c, Fq d) { return Fq::mul2_add(a, b, c, d); }
 __device__ __noinline__ Fq fq_mul4_add_call(Fq a, Fq b, Fq c, Fq d, Fq e, Fq f, Fq g, Fq h) { return Fq::mul4_add(a, b, c, d, e, f, g, h); }
 
 struct PairLane {
@@ -715,14 +711,6 @@ struct PairLane {
     const Fq nc = Fq::neg(c);
     return fq_mul4_add_call(sel(pa, a), b, sel(a, Fq::neg(pa)), pb, sel(Fq::neg(pc), nc), d, sel(nc, pc), pd);
   }
-  // two independent products (a b, c d) in one call
-  B2_D FqPair mul_x2(const Fq& a, const Fq& pa, const Fq& b, const Fq& pb, const Fq& c, const Fq& pc, const Fq& d, const Fq& pd) const {
-    return fq_mul2_add_x2_call(a, sel(pb, b), sel(pa, Fq::neg(pa)), sel(b, pb), c, sel(pd, d), sel(pc, Fq::neg(pc)), sel(d, pd));
-  }
-  // two independent squares (a^2, c^2) in one call
-  B2_D FqPair sqr_x2(const Fq& a, const Fq& pa, const Fq& c, const Fq& pc) const {
-    return fq_mul_x2_call(sel(Fq::dbl(a), Fq::add(a, pa)), sel(pa, Fq::sub(a, pa)), sel(Fq::dbl(c), Fq::add(c, pc)), sel(pc, Fq::sub(c, pc)));
-  }
   B2_D Fq one() const { return hi ? Fq::zero() : Fq::one(); }
 };
 struct XYZZHalf { Fq x, y, zz, zzz; };  // one component of an XYZZ<Fq2>
@@ -745,23 +733,24 @@ B2_D void pair_add_mixed(const PairLane& L, XYZZHalf& acc, const Fq& x2, const F
   if (L.both(x2.is_zero() && y2.is_zero())) return;
   if (L.both(acc.zz.is_zero())) { acc.x = x2; acc.y = y2; acc.zz = L.one(); acc.zzz = L.one(); return; }
   const Fq pzz = L.partner(acc.zz), pzzz = L.partner(acc.zzz);
-  const FqPair us = L.mul_x2(x2, L.partner(x2), acc.zz, pzz, y2, L.partner(y2), acc.zzz, pzzz);  // U2 | S2
-  const Fq P = Fq::sub(us.r0, acc.x), R = Fq::sub(us.r1, acc.y);
+  const Fq U2 = L.mul(x2, L.partner(x2), acc.zz, pzz), S2 = L.mul(y2, L.partner(y2), acc.zzz, pzzz);
+  const Fq P = Fq::sub(U2, acc.x), R = Fq::sub(S2, acc.y);
   if (L.both(P.is_zero())) {
     if (L.both(R.is_zero())) pair_mdbl(L, acc, x2, y2);
     else { acc.x = Fq::zero(); acc.y = Fq::zero(); acc.zz = Fq::zero(); acc.zzz = Fq::zero(); }
     return;
   }
-  const Fq pP = L.partner(P), pR = L.partner(R);
-  const FqPair sq = L.sqr_x2(P, pP, R, pR);  // PP | R^2
-  const Fq PP = sq.r0, pPP = L.partner(PP);
-  const FqPair pq = L.mul_x2(P, pP, PP, pPP, acc.x, L.partner(acc.x), PP, pPP);  // PPP | Q
-  const Fq PPP = pq.r0, pPPP = L.partner(PPP), Q = pq.r1;
-  const Fq x3 = Fq::sub(Fq::sub(sq.r1, PPP), Fq::dbl(Q));
+  const Fq pP = L.partner(P);
+  const Fq PP = L.sqr(P, pP), pPP = L.partner(PP);
+  const Fq PPP = L.mul(P, pP, PP, pPP), pPPP = L.partner(PPP);
+  const Fq Q = L.mul(acc.x, L.partner(acc.x), PP, pPP);
+  const Fq pR = L.partner(R);
+  const Fq x3 = Fq::sub(Fq::sub(L.sqr(R, pR), PPP), Fq::dbl(Q));
   const Fq T = Fq::sub(Q, x3), pT = L.partner(T);
-  const Fq y3 = L.mul2_sub(R, pR, T, pT, acc.y, L.partner(acc.y), PPP, pPPP);
-  const FqPair zz = L.mul_x2(acc.zz, pzz, PP, pPP, acc.zzz, pzzz, PPP, pPPP);  // ZZ3 | ZZZ3
-  acc.x = x3; acc.y = y3; acc.zz = zz.r0; acc.zzz = zz.r1;
+  acc.y = L.mul2_sub(R, pR, T, pT, acc.y, L.partner(acc.y), PPP, pPPP);
+  acc.x = x3;
+  acc.zz = L.mul(acc.zz, pzz, PP, pPP);
+  acc.zzz = L.mul(acc.zzz, pzzz, PPP, pPPP);
 }
 
 // one thread PAIR per slice of kSegLen sorted entries; blockDim.x threads = blockDim.x / 2 slices
@@ -801,12 +790,19 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_g2_pair(const void* 
     store_fe<Fq>(partials, w, a.x); store_fe<Fq>(partials, w + 2, a.y); store_fe<Fq>(partials, w + 4, a.zz); store_fe<Fq>(partials, w + 6, a.zzz);
   };
   XYZZHalf acc = {Fq::zero(), Fq::zero(), Fq::zero(), Fq::zero()};
+  // The next point is prefetched into L2 (prefetch.global.L2), not into registers: with the 16 registers of a register
+  // prefetch the kernel needs 168+ registers; an addition (~1800 wide multiplies per lane) is long enough for the other
+  // warps to cover an L2 hit (measured: accumulation 110.3 -> 106.2 ms at 2^24).
+  auto prefetch_half = [&](uint32_t v) {
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(points) + (4 * (size_t)(v & 0x7fffffffu) + comp) * 32;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 64));
+  };
   uint32_t v = __ldg(idx + e0);
-  Fq px, py;
-  load_half(v, px, py);
+  prefetch_half(v);
   for (uint32_t e = e0; e < e1; ++e) {
-    uint32_t vn = v; Fq nx = px, ny = py;
-    if (e + 1 < e1) { vn = __ldg(idx + e + 1); load_half(vn, nx, ny); }  // next gather in flight during the addition
+    uint32_t vn = v;
+    if (e + 1 < e1) { vn = __ldg(idx + e + 1); prefetch_half(vn); }
     if (e == next) {  // bucket boundary: close the run
       store_half(slot, acc);
       if (!L.hi) run_bucket[slot] = g;
@@ -815,9 +811,11 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate_g2_pair(const void* 
       g = bucket_of(offsets, G, g + 1, e);
       next = __ldg(offsets + g + 1);
     }
+    Fq px, py;
+    load_half(v, px, py);
     if (v >> 31) py = Fq::neg(py);  // -(y0 + y1 u) = -y0 + (-y1) u: component-wise
     pair_add_mixed(L, acc, px, py);
-    v = vn; px = nx; py = ny;
+    v = vn;
   }
   store_half(slot, acc);
   if (!L.hi) run_bucket[slot] = g;
@@ -1186,10 +1184,10 @@ static inline void phase_mark(b200zk_ctx* ctx, int k, cudaStream_t st) {
 
 // ---- accumulation launch: G1 one thread per slice; G2 one lane PAIR per slice (msm_accumulate_g2_pair) unless the knob says otherwise
 static int g2_pair_knob() {
-  // experiment knob B200ZK_G2_PAIR=0: the one-thread-per-slice G2 kernel; 2 | 3 | 4: CTAs per SM the lane-pair kernel is
-  // compiled for (203 registers uncapped / 168 / 128)
+  // experiment knob B200ZK_G2_PAIR=0: the one-thread-per-slice G2 kernel; 3 | 4: CTAs per SM the lane-pair kernel is
+  // compiled for (154 registers, no spills | 128 registers, spills).  Default 3 (measured: 106.2 | 107.0 ms at 2^24)
   static int k = -1;
-  if (k < 0) { const char* e = getenv("B200ZK_G2_PAIR"); k = (e && *e >= '0' && *e <= '4' && *e != '1') ? (*e - '0') : 3; }
+  if (k < 0) { const char* e = getenv("B200ZK_G2_PAIR"); k = (e && (*e == '0' || *e == '3' || *e == '4')) ? (*e - '0') : 3; }
   return k;
 }
 template <class F> static size_t resident_slices(const b200zk_ctx* ctx) {
@@ -1203,8 +1201,7 @@ static int launch_accumulate(b200zk_ctx* ctx, cudaStream_t st, const void* pts, 
   if constexpr (IsFq2<F>::value) {
     const int k = g2_pair_knob();
     const unsigned pgrid = (unsigned)((2 * slices + 127) / 128);
-    if (k == 2) B2_LAUNCH(ctx, msm_accumulate_g2_pair<2>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
-    else if (k == 3) B2_LAUNCH(ctx, msm_accumulate_g2_pair<3>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
+    if (k == 3) B2_LAUNCH(ctx, msm_accumulate_g2_pair<3>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
     else if (k == 4) B2_LAUNCH(ctx, msm_accumulate_g2_pair<4>, pgrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
     else B2_LAUNCH(ctx, (msm_accumulate<F, false, 1>), agrid, 128, 0, st, pts, idx, offsets, run_off, G, L, partials, run_bucket);
   } else {

@@ -144,3 +144,43 @@ def test_host_buffer_length_guard():
         _need(bytes(63), 64, "x")
     with pytest.raises(eb.B200Error):
         _need(np.zeros(7, dtype=np.uint64), 64, "x")
+
+
+def test_kzg_host_bookkeeping_without_a_gpu():
+    """ethrex_b200/kzg.py's scalar-field work (barycentric evaluation, quotient in evaluation form, the in-domain special
+    case, the Fiat-Shamir challenge) with the two MSMs served in the exponent by a stand-in context: the commitment must be
+    p(tau) G and the proof ((p(tau) - p(z)) / (tau - z)) G for a synthetic Lagrange setup (device half: tests/test_gpu_bls.py)."""
+    import bls_ref as bls
+    from ethrex_b200.kzg import KzgSettings, roots_of_unity_brp
+    tau = 0x123456789ABCDEF0FEDCBA9876543210 % bls.R
+    lag = bls.lagrange_setup_scalars(tau)
+
+    class ExponentCtx:
+        def bls12_381_g1_bases_upload(self, pts, n, flags=0): return 1
+        def bases_precompute(self, h, c): pass
+        def bases_free(self, h): pass
+        def _dot(self, raw):
+            return sum(int.from_bytes(raw[32 * i:32 * i + 32], "big") * l for i, l in enumerate(lag)) % bls.R
+        def kzg_blob_to_commitment(self, h, blobs): return [bls.compress(bls.mul(self._dot(blobs[k * 131072:(k + 1) * 131072]), bls.G1)) for k in range(len(blobs) // 131072)]
+        def bls12_381_g1_msm_resident(self, h, scalars, n, flags=0): return bls.compress(bls.mul(self._dot(scalars), bls.G1))
+
+    st = KzgSettings(ExponentCtx(), bytes(48 * 4096), precompute=True)
+    rng = np.random.default_rng(7)
+    vals = [int.from_bytes(rng.bytes(32), "big") % bls.R for _ in range(4096)]
+    blob = b"".join(v.to_bytes(32, "big") for v in vals)
+    p_tau = sum(v * l for v, l in zip(vals, lag)) % bls.R
+    c, proof = st.blob_to_kzg_commitment_and_proof(blob)
+    assert c == bls.compress(bls.mul(p_tau, bls.G1))
+    z = st.compute_challenge(blob, c)
+    proof_z, y = st.compute_kzg_proof(blob, z)
+    assert proof_z == proof
+    # y = p(z): check against the definition through the Lagrange basis at z
+    lag_z = bls.lagrange_setup_scalars(z)
+    assert y == sum(v * l for v, l in zip(vals, lag_z)) % bls.R
+    assert proof == bls.compress(bls.mul((p_tau - y) * pow((tau - z) % bls.R, -1, bls.R) % bls.R, bls.G1))
+    zr = roots_of_unity_brp()[1234]
+    proof_r, yr = st.compute_kzg_proof(blob, zr)
+    assert yr == vals[1234]
+    assert proof_r == bls.compress(bls.mul((p_tau - yr) * pow((tau - zr) % bls.R, -1, bls.R) % bls.R, bls.G1))
+    with pytest.raises(ValueError):
+        st.compute_kzg_proof(bls.R.to_bytes(32, "big") + blob[32:], 5)

@@ -90,3 +90,81 @@ def test_shard_range_covers_everything():
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
     assert sorted(sum((ntt_batch_assignment(7, r, 3) for r in range(3)), [])) == list(range(7))
+
+
+# ---- the multi-GPU proof path (round 2): dealt NTTs + ONE all_gather of the 768-byte blocks + fold -------------------
+class OracleProofCtx:
+    """Quacks like ethrex_b200.Context for dist.quotient_dealt (fr_ntt_device / fr_quotient_device on CPU tensors) and for the
+    commit_partial / fold pair: a block holds A | B1 | B2 | L | H as XYZZ with ZZ = ZZZ = 1 (or all zero for the identity)."""
+    NTT_INVERSE, NTT_COSET = 1 << 4, 1 << 5  # ethrex_b200._ffi flag values
+
+    def fr_ntt_device(self, t, log_n, flags):
+        oflags = (orc.NTT_INVERSE if flags & self.NTT_INVERSE else 0) | (orc.NTT_COSET if flags & self.NTT_COSET else 0)
+        a = orc.fr_ntt(t.numpy().view(np.uint64).reshape(-1, 4), log_n, oflags)
+        t.copy_(torch.from_numpy(a.view(np.int64).reshape(-1).copy()))
+
+    def fr_quotient_device(self, a, b, c, out, n, zinv):
+        r = orc.fr_quotient(a.numpy().view(np.uint64).reshape(-1, 4), b.numpy().view(np.uint64).reshape(-1, 4), c.numpy().view(np.uint64).reshape(-1, 4), zinv)
+        out.copy_(torch.from_numpy(r.view(np.int64).reshape(-1).copy()))
+
+
+def _g1_xyzz(be: bytes) -> np.ndarray:
+    one = orc.fq_to_mont(orc.ints_to_array([1])).reshape(-1)
+    if be == bytes(64):
+        return np.zeros(16, dtype=np.uint64)
+    return np.concatenate([orc.g1_be_to_native(be).reshape(-1), one, one])
+
+
+def _proof_worker(rank, world, port, log_n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ethrex_b200.dist import quotient_dealt
+        from ethrex_b200.groth16 import coset_vanishing_inverse
+        n = 1 << log_n
+        a = orc.fr_to_mont(orc.rand_fr(11, 0, n)); b = orc.fr_to_mont(orc.rand_fr(12, 0, n)); c = orc.field_mul("fr", a, b)
+        ta, tb, tc = (torch.from_numpy(x.view(np.int64).reshape(-1).copy()) for x in (a, b, c))
+        h = quotient_dealt(OracleProofCtx(), log_n, ta, tb, tc, coset_vanishing_inverse(log_n), rank, world)
+        h_can = orc.fr_from_mont(h.numpy().view(np.uint64).reshape(n, 4))
+        # this rank's slice of one proving-key column against its slice of H, as a block; ONE all_gather; fold on every rank
+        k, d = pyref.chain_scalar(pyref.SEED_POINTS)
+        lo, hi = shard_range(n, rank, world)
+        hi_h = min(hi, n - 1)
+        part = orc.g1_msm(orc.g1_chain(n, k, d)[lo:hi_h], h_can[lo:hi_h]) if hi_h > lo else bytes(64)
+        block = torch.zeros(96, dtype=torch.int64)
+        block[80:96] = torch.from_numpy(_g1_xyzz(part).view(np.int64).copy())  # the H slot of A | B1 | B2 | L | H (bytes 640..767)
+        gathered = torch.empty(96 * world, dtype=torch.int64)
+        dist.all_gather_into_tensor(gathered, block)
+        acc = bytes(64)
+        g = gathered.numpy().view(np.uint64).reshape(world, 96)
+        for r in range(world):
+            x = g[r, 80:96]
+            acc = orc.g1_add_be(acc, bytes(64) if not x[8:].any() else orc.g1_native_to_be(x[:8]))[1]
+        q.put((rank, h_can.tobytes(), acc))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dealt_quotient_and_block_fold_world2_gloo():
+    """dist.quotient_dealt on 2 ranks = the single-process quotient; the per-rank H commitments, all-gathered as 768-byte
+    blocks and folded, = the whole-column MSM (the host plumbing of SyntheticWrapCircuit.prove_device for world > 1)."""
+    from ethrex_b200.groth16 import coset_vanishing_inverse
+    log_n, world, port = 8, 2, _free_port()
+    n = 1 << log_n
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_proof_worker, args=(r, world, port, log_n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {r: (h, acc) for r, h, acc in (q.get(timeout=180) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a = orc.fr_to_mont(orc.rand_fr(11, 0, n)); b = orc.fr_to_mont(orc.rand_fr(12, 0, n)); c = orc.field_mul("fr", a, b)
+    cos = [orc.fr_ntt(orc.fr_ntt(p, log_n, orc.NTT_INVERSE), log_n, orc.NTT_COSET) for p in (a, b, c)]
+    h = orc.fr_from_mont(orc.fr_ntt(orc.fr_quotient(cos[0], cos[1], cos[2], coset_vanishing_inverse(log_n)), log_n, orc.NTT_INVERSE | orc.NTT_COSET))
+    assert res[0][0] == res[1][0] == h.tobytes()
+    assert orc.array_to_ints(h)[n - 1] == 0  # the quotient is exact
+    k, d = pyref.chain_scalar(pyref.SEED_POINTS)
+    whole = orc.g1_msm(orc.g1_chain(n, k, d)[:n - 1], h[:n - 1])
+    assert res[0][1] == res[1][1] == whole

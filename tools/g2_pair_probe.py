@@ -31,7 +31,7 @@ for log_n in (22, 24):
     print(json.dumps({"probe": "g2_pair", "knob": os.environ.get("B200ZK_G2_PAIR", "default"), "log_n": log_n, "msm_ms": ms, "phases": acc[-1], "result": out.hex()[:32]}), flush=True)
     ctx.bases_free(h); del sc; torch.cuda.empty_cache()
 ''' % (ROOT, os.path.join(ROOT, "oracle"))
-for knob in ("0", "2", "3", "4"):
+for knob in ("0", "3", "4"):
     env = dict(os.environ, B200ZK_G2_PAIR=knob)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout)
