@@ -17,6 +17,7 @@ WANT = {
     "dram__bytes_write.sum": "dram_bytes_write",
     "gpu__time_duration.sum": "duration",
     "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active": "fmaheavy_pct",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed": "fmaheavy_pct_elapsed",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "alu_pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
@@ -48,6 +49,8 @@ def read_rows(path):
                     v = float(r[j].replace(",", ""))
                 except ValueError:
                     continue
+                if v != v:  # nan ("n/a" for a metric the kernel does not exercise)
+                    continue
                 row[key] = v * UNIT_SCALE.get(units[j], 1.0)
         out.append(row)
     return out
@@ -64,8 +67,8 @@ def main():
         m = [r for r in rows if pred(r["kernel"])]
         return m[-1] if m else None
 
-    g1 = last(lambda k: "msm_accumulate" in k and "Fq2" not in k and "FqCfg" in k or ("msm_accumulate" in k and "Fq2" not in k))
-    g2 = last(lambda k: "msm_accumulate" in k and "Fq2" in k)
+    g1 = last(lambda k: "msm_accumulate<" in k and "Fq2" not in k and "Fp381" not in k)
+    g2 = last(lambda k: "msm_accumulate_g2_pair" in k or ("msm_accumulate<" in k and "Fq2" in k))
     if g1:
         kernels["msm_accumulate_g1"] = g1
     if g2:
@@ -81,8 +84,9 @@ def main():
         for key in ("dram_bytes_read", "dram_bytes_write", "duration", "instructions"):
             if all(key in p for p in passes):
                 tot[key] = sum(p[key] for p in passes)
-        if all("fmaheavy_pct" in p and "duration" in p for p in passes):
-            tot["fmaheavy_pct"] = sum(p["fmaheavy_pct"] * p["duration"] for p in passes) / sum(p["duration"] for p in passes)
+        for key in ("fmaheavy_pct", "fmaheavy_pct_elapsed"):
+            if all(key in p and "duration" in p for p in passes):
+                tot[key] = sum(p[key] * p["duration"] for p in passes) / sum(p["duration"] for p in passes)
         kernels["ntt_forward_2_24"] = tot
     doc = {"source_hash": bench.source_hash(), "captured_from": os.path.basename(src),
            "how": "ncu --set full --clock-control none python tools/profile_workload.py (2^24 G1 MSM, G2 MSM over window tables, forward NTT); durations in ms, "
@@ -91,7 +95,7 @@ def main():
     with open(dst, "w") as f:
         json.dump(doc, f, indent=1)
     for k, v in kernels.items():
-        print(k, {x: v[x] for x in ("duration", "dram_bytes_read", "dram_bytes_write", "fmaheavy_pct", "registers") if x in v})
+        print(k, {x: v[x] for x in ("duration", "dram_bytes_read", "dram_bytes_write", "fmaheavy_pct", "fmaheavy_pct_elapsed", "registers") if x in v})
 
 
 if __name__ == "__main__":
