@@ -215,13 +215,14 @@ void b200zk_destroy(b200zk_ctx* ctx) {
   if (ctx->ws_zinv.p) cudaFree(ctx->ws_zinv.p);
   if (ctx->ws_key.p) cudaFree(ctx->ws_key.p);
   if (ctx->ws_ctab.p) cudaFree(ctx->ws_ctab.p);
+  if (ctx->ws_cnt2.p) cudaFree(ctx->ws_cnt2.p);
   DevBuf* bufs[] = {&ctx->ws_hist, &ctx->ws_offsets, &ctx->ws_cursor, &ctx->ws_blocksums, &ctx->ws_idx, &ctx->ws_buckets, &ctx->ws_chunkS,
                     &ctx->ws_chunkV, &ctx->ws_result, &ctx->ws_points, &ctx->ws_scalars, &ctx->ws_ntt, &ctx->ws_misc, &ctx->ws_out, &ctx->ws_segoff, &ctx->ws_segbucket, &ctx->ws_digits, &ctx->ws_q0, &ctx->ws_q1, &ctx->ws_prefix, &ctx->ws_info, &ctx->ws_pairoff0, &ctx->ws_pairoff1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->ws_totals.p) cudaFree(ctx->ws_totals.p);
   if (ctx->ws_bitpart.p) cudaFree(ctx->ws_bitpart.p);
   for (auto& sl : ctx->slot) {
-    DevBuf* sb[] = {&sl.hist, &sl.offsets, &sl.cursor, &sl.run_off, &sl.tsum, &sl.digits, &sl.idx, &sl.key, &sl.ctab};
+    DevBuf* sb[] = {&sl.hist, &sl.offsets, &sl.cursor, &sl.run_off, &sl.tsum, &sl.digits, &sl.idx, &sl.key, &sl.ctab, &sl.cnt2};
     for (DevBuf* b : sb) if (b->p) cudaFree(b->p);
     if (sl.sorted) cudaEventDestroy(sl.sorted);
     if (sl.released) cudaEventDestroy(sl.released);

@@ -32,7 +32,7 @@ struct TwiddleSet {   // per (log_n, direction): see ntt.cu
 };
 
 struct SortSlot {  // one of the two sort workspaces of the chunk-pipelined MSM
-  DevBuf hist, offsets, cursor, run_off, tsum, digits, idx, key, ctab;
+  DevBuf hist, offsets, cursor, run_off, tsum, digits, idx, key, ctab, cnt2;
   cudaEvent_t sorted = nullptr, released = nullptr;
 };
 
@@ -59,7 +59,7 @@ struct b200zk_ctx {
   cudaEvent_t ev_up[64] = {};  // upload k of the chunk-pipelined MSM has landed (recorded on stream_sort, waited on by the caller's stream)
   b200zk::SortSlot slot[2];
   b200zk::DevBuf ws_totals, ws_bitpart;
-  b200zk::DevBuf ws_key, ws_ctab;  // two-level sort: 16-bit fine keys of the coarse-partitioned entries; per-(bin, CTA) counts / bases
+  b200zk::DevBuf ws_key, ws_ctab, ws_cnt2;  // two-level sort: 16-bit fine keys of the coarse-partitioned entries; per-(bin, CTA) counts / bases
   b200zk::DevBuf ws_g16[4];   // b200zk_groth16_commit: staged A/B/C evaluations (host inputs) and the 768-byte partial block
   b200zk::DevBuf ws_zinv;     // 1/(5^n - 1) of the last quotient domain, canonical limbs (cached per log_n)
   uint32_t zinv_log_n = 0xffffffffu;

@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(256) msm_scatter(const uint32_t* __restrict__ 
 //   msm_sort_coarse  the same CTA walks the same scalars in tiles of 1024; a tile's entries are ranked per bin with
 //                    shared-memory atomics, permuted in shared memory, and copied out so that adjacent lanes write adjacent
 //                    addresses (one 8-byte word per entry: value | fine key) -- no global atomics, runs instead of scattered stores
-//   msm_sort_fine    one CTA per coarse bin: fine histogram in shared memory (-> the bucket offsets and counts the
-//                    accumulation needs, for free), then the final placement with shared-memory cursors; the bin's output
-//                    region is a few MB, so its 4-byte stores combine in L2
+//   msm_sort_fine_*  the bins are cut into segments of 32768 entries (balanced whatever the bin sizes): per-segment fine
+//                    histograms in shared memory, a column prefix over each bin's segments (-> the bucket counts, then the
+//                    bucket offsets by the ordinary scan), and the final placement staged through shared memory so that a
+//                    bucket's entries leave as one run
 // Order inside a bucket is not deterministic (shared-memory atomics); the sum is.
 static constexpr uint32_t kSortTile = 1024;        // scalars per coarse tile = threads of msm_sort_coarse
 static constexpr uint32_t kSortMaxW = 16;          // windows per scalar the staging buffers are sized for (c >= 16)
@@ -414,19 +415,24 @@ __global__ void __launch_bounds__(kSortTile, 1) msm_sort_coarse(const void* __re
   }
 }
 
-// grid = C (one CTA per coarse bin), block = 1024.  bin b holds entries [base[b * NC], base[(b + 1) * NC]) of ent1.
-// Writes hist[g], offsets[g] for its buckets, offsets[G] (last bin) and the final idx.
-// The placement is staged like the coarse pass: a tile of kFineTile entries is ranked per key in shared memory, permuted
-// there, and copied out so that the entries of one bucket leave as one run (ncu r2d of the direct version -- one scattered
-// 4-byte store per entry -- showed the L2 tag lookups as the limit: lts__t_tag_requests 47 % at 2.2 ms).
-static constexpr uint32_t kFineTile = 8192;  // entries per tile = 8 per thread
+// ---- fine pass, balanced: work items are SEGMENTS of kFineSeg entries of a coarse bin ------------------------------------
+// One CTA per coarse bin (the first r2 version) is as unbalanced as the bins are -- and they are: the top window of a
+// 254-bit scalar only has 254 - 240 = 14 bits at c = 20, so all of its 2^24 entries land in the 16 lowest bins (3.5x the
+// average; at c = 19 / 21 / 22 in one or two bins: 12-13 ms), and skewed witnesses do the same to any bin.  Now:
+//   msm_sort_items     item_start[b] = sum_{b' < b} ceil(size(b') / kFineSeg)                          (one small CTA)
+//   msm_sort_fine_count  item i = (bin, segment): histogram of its entries' fine keys -> cnt2[i][key]
+//   msm_sort_fine_prefix thread (bin, key): exclusive prefix of cnt2[.][key] over the bin's segments, total -> hist[g]
+//   (scan of hist -> offsets, the kernels the legacy sort used)
+//   msm_sort_fine_place  item i: cursor[key] = offsets[g] + cnt2[i][key]; staged placement of its segment
+static constexpr uint32_t kFineTile = 8192;   // entries per staged tile = 8 per thread
+static constexpr uint32_t kFineSeg = 4 * kFineTile;  // entries per work item
 struct SortFineSmem {
   uint32_t val[kFineTile], dst[kFineTile];
-  uint32_t fh[kSortMaxFine], cur[kSortMaxFine], tcnt[kSortMaxFine], tstart[kSortMaxFine];
+  uint32_t cur[kSortMaxFine], tcnt[kSortMaxFine], tstart[kSortMaxFine];
   uint32_t warp_tot[32];
   uint32_t total;
 };
-// exclusive scan of in[0..F) (F <= 2048, two keys per thread of a 1024-thread CTA) into out; returns nothing, leaves the grand total in *total
+// exclusive scan of in[0..F) (F <= 2048, two keys per thread of a 1024-thread CTA) into out; leaves the grand total in *total
 B2_D void scan_fine_keys(const uint32_t* in, uint32_t* out, uint32_t F, uint32_t* warp_tot, uint32_t* total) {
   const uint32_t tid = threadIdx.x, k0 = 2 * tid, k1 = 2 * tid + 1;
   const uint32_t v0 = k0 < F ? in[k0] : 0, v1 = k1 < F ? in[k1] : 0;
@@ -443,37 +449,86 @@ B2_D void scan_fine_keys(const uint32_t* in, uint32_t* out, uint32_t F, uint32_t
   if (tid == 1023) *total = wb + incl;
   __syncthreads();
 }
-__global__ void __launch_bounds__(1024, 1) msm_sort_fine(const uint2* __restrict__ ent1, SortPlan sp, const uint32_t* __restrict__ base,
-                                                         uint32_t* __restrict__ hist, uint32_t* __restrict__ offsets, uint32_t* __restrict__ idx) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  SortFineSmem& sm = *reinterpret_cast<SortFineSmem*>(smem_raw);
-  const uint32_t b = blockIdx.x, tid = threadIdx.x, F = 1u << sp.fb;
-  const uint32_t bs = __ldg(base + (size_t)b * sp.NC), be = __ldg(base + (size_t)(b + 1) * sp.NC);
-  for (uint32_t k = tid; k < F; k += 1024) { sm.fh[k] = 0; sm.tcnt[k] = 0; }
+// one CTA of 1024 threads: item_start[0..C] (C <= 1024)
+__global__ void __launch_bounds__(1024) msm_sort_items(const uint32_t* __restrict__ base, SortPlan sp, uint32_t* __restrict__ item_start) {
+  __shared__ uint32_t wt[32];
+  const uint32_t tid = threadIdx.x;
+  uint32_t v = 0;
+  if (tid < sp.C) { const uint32_t sz = __ldg(base + (size_t)(tid + 1) * sp.NC) - __ldg(base + (size_t)tid * sp.NC); v = (sz + kFineSeg - 1) / kFineSeg; }
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= (unsigned)o) incl += t; }
+  if ((tid & 31) == 31) wt[tid >> 5] = incl;
   __syncthreads();
-  // ---- histogram of the bin's fine keys (kFineIlp independent loads in flight per thread)
-  for (uint32_t e0 = bs + tid; e0 < be; e0 += 1024 * kFineIlp) {
+  uint32_t wb = 0;
+  for (uint32_t k = 0; k < (tid >> 5); ++k) wb += wt[k];
+  if (tid < sp.C) item_start[tid] = wb + incl - v;
+  if (tid == sp.C - 1) item_start[sp.C] = wb + incl;
+}
+// the bin of item i: largest b with item_start[b] <= i (items of empty bins do not exist: item_start repeats)
+B2_D uint32_t item_bin(const uint32_t* __restrict__ item_start, uint32_t C, uint32_t i) {
+  uint32_t lo = 0, hi = C;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(item_start + mid) <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+__global__ void __launch_bounds__(1024, 2) msm_sort_fine_count(const uint2* __restrict__ ent1, SortPlan sp, const uint32_t* __restrict__ base, const uint32_t* __restrict__ item_start,
+                                                               uint32_t* __restrict__ cnt2) {
+  __shared__ uint32_t fh[kSortMaxFine];
+  const uint32_t i = blockIdx.x, tid = threadIdx.x, F = 1u << sp.fb;
+  if (i >= __ldg(item_start + sp.C)) return;
+  const uint32_t b = item_bin(item_start, sp.C, i);
+  const uint32_t bs = __ldg(base + (size_t)b * sp.NC), be = __ldg(base + (size_t)(b + 1) * sp.NC);
+  const uint32_t s0 = bs + (i - __ldg(item_start + b)) * kFineSeg, s1 = (be - s0 > kFineSeg) ? s0 + kFineSeg : be;
+  for (uint32_t k = tid; k < F; k += 1024) fh[k] = 0;
+  __syncthreads();
+  for (uint32_t e0 = s0 + tid; e0 < s1; e0 += 1024 * kFineIlp) {
     uint32_t kk[kFineIlp];
 #pragma unroll
-    for (int u = 0; u < kFineIlp; ++u) { const uint32_t e = e0 + u * 1024; kk[u] = e < be ? __ldg(&ent1[e].y) : 0xffffffffu; }
+    for (int u = 0; u < kFineIlp; ++u) { const uint32_t e = e0 + u * 1024; kk[u] = e < s1 ? __ldg(&ent1[e].y) : 0xffffffffu; }
 #pragma unroll
-    for (int u = 0; u < kFineIlp; ++u) if (kk[u] != 0xffffffffu) atomicAdd(&sm.fh[kk[u]], 1u);
+    for (int u = 0; u < kFineIlp; ++u) if (kk[u] != 0xffffffffu) atomicAdd(&fh[kk[u]], 1u);
   }
   __syncthreads();
-  scan_fine_keys(sm.fh, sm.cur, F, sm.warp_tot, &sm.total);  // cur[k] = first slot (relative to bs) of key k
+  for (uint32_t k = tid; k < F; k += 1024) cnt2[(size_t)i * F + k] = fh[k];
+}
+// grid = C * F / 256 threads: thread (b, key) turns cnt2[item][key] into its exclusive prefix over the bin's items
+__global__ void __launch_bounds__(256) msm_sort_fine_prefix(SortPlan sp, const uint32_t* __restrict__ item_start, uint32_t* __restrict__ cnt2, uint32_t* __restrict__ hist) {
+  const uint32_t F = 1u << sp.fb;
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= (size_t)sp.C * F) return;
+  const uint32_t b = (uint32_t)(t >> sp.fb), k = (uint32_t)t & (F - 1);
+  const uint32_t i0 = __ldg(item_start + b), i1 = __ldg(item_start + b + 1);
+  uint32_t run = 0;
+  for (uint32_t i = i0; i < i1; ++i) {
+    const size_t at = (size_t)i * F + k;
+    const uint32_t c = cnt2[at];
+    cnt2[at] = run;
+    run += c;
+  }
+  if (t < sp.G) hist[t] = run;
+}
+__global__ void __launch_bounds__(1024, 1) msm_sort_fine_place(const uint2* __restrict__ ent1, SortPlan sp, const uint32_t* __restrict__ base, const uint32_t* __restrict__ item_start,
+                                                               const uint32_t* __restrict__ cnt2, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SortFineSmem& sm = *reinterpret_cast<SortFineSmem*>(smem_raw);
+  const uint32_t i = blockIdx.x, tid = threadIdx.x, F = 1u << sp.fb;
+  if (i >= __ldg(item_start + sp.C)) return;
+  const uint32_t b = item_bin(item_start, sp.C, i);
+  const uint32_t bs = __ldg(base + (size_t)b * sp.NC), be = __ldg(base + (size_t)(b + 1) * sp.NC);
+  const uint32_t s0 = bs + (i - __ldg(item_start + b)) * kFineSeg, s1 = (be - s0 > kFineSeg) ? s0 + kFineSeg : be;
   for (uint32_t k = tid; k < F; k += 1024) {
     const size_t g = (size_t)b * F + k;
-    if (g < sp.G) { offsets[g] = bs + sm.cur[k]; hist[g] = sm.fh[k]; }
+    sm.cur[k] = (g < sp.G ? __ldg(offsets + g) : 0u) + __ldg(cnt2 + (size_t)i * F + k);  // absolute slot of this item's first entry of key k
+    sm.tcnt[k] = 0;
   }
-  if (b == gridDim.x - 1 && tid == 0) offsets[sp.G] = be;  // total number of entries
-  // ---- placement, tile by tile
-  for (uint32_t t0 = bs; t0 < be; t0 += kFineTile) {
+  __syncthreads();
+  for (uint32_t t0 = s0; t0 < s1; t0 += kFineTile) {
     uint2 ev[kFineTile / 1024];
     uint32_t rank[kFineTile / 1024];
 #pragma unroll
     for (int u = 0; u < (int)(kFineTile / 1024); ++u) {
       const uint32_t e = t0 + u * 1024 + tid;
-      ev[u] = e < be ? __ldg(ent1 + e) : make_uint2(0u, 0xffffffffu);
+      ev[u] = e < s1 ? __ldg(ent1 + e) : make_uint2(0u, 0xffffffffu);
     }
 #pragma unroll
     for (int u = 0; u < (int)(kFineTile / 1024); ++u) rank[u] = ev[u].y != 0xffffffffu ? atomicAdd(&sm.tcnt[ev[u].y], 1u) : 0u;
@@ -484,7 +539,7 @@ __global__ void __launch_bounds__(1024, 1) msm_sort_fine(const uint2* __restrict
       if (ev[u].y != 0xffffffffu) {
         const uint32_t pos = sm.tstart[ev[u].y] + rank[u];
         sm.val[pos] = ev[u].x;
-        sm.dst[pos] = bs + sm.cur[ev[u].y] + rank[u];
+        sm.dst[pos] = sm.cur[ev[u].y] + rank[u];
       }
     __syncthreads();
     const uint32_t total = sm.total;
@@ -584,6 +639,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, c
 // radix-kTreeRadix tree in place, leaving each bucket's total in its first run.
 static constexpr uint32_t kSegLenMax = 256;  // the slice length itself is a launch parameter (wave balancing)
 static constexpr uint32_t kTreeRadix = 64;
+// Buckets with at most kDirectRuns runs are NOT folded by partial_tree: their consumers (bucket_chunk, bucket_merge) add
+// the runs themselves.  With slices of ~240 entries and buckets of ~416 (c = 20 at 2^24) nearly every bucket has 2-3 runs:
+// folding them in the tree kernel kept one lane in 2.6 busy (0.73 ms per G1 MSM, ncu r2); the consumers walk buckets
+// anyway.  The tree only remains for heavy buckets (skewed scalars).
+static constexpr uint32_t kDirectRuns = 4;
 
 // Slice length for M entries: every thread does the same work, so the launch runs in lock-step "waves" of
 // `resident` threads; pick the length that fills a whole number of waves instead of leaving the last one part empty.
@@ -962,7 +1022,7 @@ __global__ void __launch_bounds__(128) partial_tree(const uint32_t* __restrict__
   if (s >= __ldg(seg_off + G)) return;
   const uint32_t g = seg_bucket[s];
   const uint32_t base = __ldg(seg_off + g), ns = __ldg(seg_off + g + 1) - base, j = s - base;
-  if (ns <= stride || (j % (stride * kTreeRadix)) != 0) return;
+  if (ns <= kDirectRuns || ns <= stride || (j % (stride * kTreeRadix)) != 0) return;
   XYZZ<F> acc = load_xyzz<F>(partials, s);
   for (uint32_t t = 1; t < kTreeRadix; ++t) {
     uint32_t jj = j + t * stride;
@@ -973,17 +1033,27 @@ __global__ void __launch_bounds__(128) partial_tree(const uint32_t* __restrict__
   store_xyzz(partials, s, acc);
 }
 
+// total of a non-empty bucket whose runs start at `so`: its first run (already folded by partial_tree when it had more than
+// kDirectRuns runs), else the sum of its `cnt` runs
+template <class F> B2_D XYZZ<F> bucket_total(const void* __restrict__ partials, uint32_t so, uint32_t cnt) {
+  XYZZ<F> b = load_xyzz<F>(partials, so);
+  if (cnt <= kDirectRuns)
+    for (uint32_t r = 1; r < cnt; ++r) { XYZZ<F> q = load_xyzz<F>(partials, so + r); xyzz_add(b, q); }
+  return b;
+}
+
 // totals[g] (+)= this chunk's total of bucket g (its first run after partial_tree); first chunk initialises
 template <class F>
 __global__ void __launch_bounds__(128) bucket_merge(const void* __restrict__ partials, const uint32_t* __restrict__ run_off, uint32_t G, int first, void* __restrict__ totals) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   uint32_t so = __ldg(run_off + g);
-  bool has = __ldg(run_off + g + 1) != so;
+  const uint32_t cnt = __ldg(run_off + g + 1) - so;
+  bool has = cnt != 0;
   if (first) {
-    store_xyzz(totals, g, has ? load_xyzz<F>(partials, so) : XYZZ<F>::identity());
+    store_xyzz(totals, g, has ? bucket_total<F>(partials, so, cnt) : XYZZ<F>::identity());
   } else if (has) {
-    XYZZ<F> t = load_xyzz<F>(totals, g), p = load_xyzz<F>(partials, so);
+    XYZZ<F> t = load_xyzz<F>(totals, g), p = bucket_total<F>(partials, so, cnt);
     xyzz_add(t, p);
     store_xyzz(totals, g, t);
   }
@@ -1004,8 +1074,9 @@ __global__ void __launch_bounds__(128) bucket_chunk(const void* __restrict__ par
       xyzz_add(run, b);
     } else {
       uint32_t so = __ldg(seg_off + first + k);
-      if (__ldg(seg_off + first + k + 1) != so) {  // non-empty bucket: its total sits in its first partial
-        XYZZ<F> b = load_xyzz<F>(partials, so);
+      const uint32_t cnt = __ldg(seg_off + first + k + 1) - so;
+      if (cnt) {  // non-empty bucket: its total is its first partial (heavy buckets, folded by partial_tree) or the sum of its few runs
+        XYZZ<F> b = bucket_total<F>(partials, so, cnt);
         xyzz_add(run, b);
       }
     }
@@ -1217,13 +1288,17 @@ static int legacy_sort_knob() {
   if (knob < 0) { const char* e = getenv("B200ZK_SORT"); knob = (e && !strcmp(e, "legacy")) ? 1 : 0; }
   return knob;
 }
+// scratch sizes of the two-level sort for up to M_max entries
+static size_t sort_ctab_bytes(int sm_count) { return (2 * ((size_t)kSortMaxBins * (size_t)sm_count + 1) + kSortMaxBins + 1) * 4; }
+static size_t sort_cnt2_bytes(size_t M_max) { return (M_max / kFineSeg + kSortMaxBins + 1) * (size_t)kSortMaxFine * 4; }
 static int run_two_level_sort(b200zk_ctx* ctx, const void* d_scalars, size_t n, uint32_t flags, const MsmPlan& pl, const SortPlan& sp, uint32_t* hist, uint32_t* offsets,
-                              uint32_t* tsum, uint2* ent1, uint32_t* ctab, uint32_t* idx, cudaStream_t st, bool mark) {
+                              uint32_t* tsum, uint2* ent1, uint32_t* ctab, uint32_t* cnt2, uint32_t* idx, cudaStream_t st, bool mark) {
   const size_t Gc = (size_t)sp.C * sp.NC, tilesC = (Gc + kScanTile - 1) / kScanTile;
-  uint32_t *cnt = ctab, *base = ctab + Gc + 1;
+  const size_t G = sp.G, tilesG = (G + kScanTile - 1) / kScanTile;
+  uint32_t *cnt = ctab, *base = ctab + Gc + 1, *item_start = base + Gc + 1;
   if (!ctx->attr_sort) {
     B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortCoarseSmem)));
-    B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortFineSmem)));
+    B2_CUDA(ctx, cudaFuncSetAttribute(msm_sort_fine_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortFineSmem)));
     ctx->attr_sort = true;
   }
   B2_CUDA(ctx, cudaMemsetAsync(cnt, 0, (Gc + 1) * 4, st));
@@ -1234,7 +1309,17 @@ static int run_two_level_sort(b200zk_ctx* ctx, const void* d_scalars, size_t n, 
   B2_LAUNCH(ctx, scan_apply, (unsigned)tilesC, kScanThreads, 0, st, (const uint32_t*)cnt, (const uint32_t*)nullptr, Gc, 0u, 0u, (const uint32_t*)tsum, base, (uint32_t*)nullptr);
   if (mark) phase_mark(ctx, 2, st);
   B2_LAUNCH(ctx, msm_sort_coarse, sp.NC, kSortTile, sizeof(SortCoarseSmem), st, d_scalars, n, flags, pl, sp, (const uint32_t*)base, ent1);
-  B2_LAUNCH(ctx, msm_sort_fine, sp.C, 1024, sizeof(SortFineSmem), st, (const uint2*)ent1, sp, (const uint32_t*)base, hist, offsets, idx);
+  // fine pass over segments of kFineSeg entries: at most M / kFineSeg + C items (the grid is this bound; surplus CTAs exit)
+  const unsigned max_items = (unsigned)((n * (size_t)pl.W) / kFineSeg + sp.C + 1);
+  const uint32_t F = 1u << sp.fb;
+  B2_LAUNCH(ctx, msm_sort_items, 1, 1024, 0, st, (const uint32_t*)base, sp, item_start);
+  B2_LAUNCH(ctx, msm_sort_fine_count, max_items, 1024, 0, st, (const uint2*)ent1, sp, (const uint32_t*)base, (const uint32_t*)item_start, cnt2);
+  B2_LAUNCH(ctx, msm_sort_fine_prefix, (unsigned)(((size_t)sp.C * F + 255) / 256), 256, 0, st, sp, (const uint32_t*)item_start, cnt2, hist);
+  B2_LAUNCH(ctx, scan_tile_sums, (unsigned)tilesG, kScanThreads, 0, st, (const uint32_t*)hist, (const uint32_t*)nullptr, G, 0u, 0u, tsum);
+  B2_LAUNCH(ctx, scan_tile_offsets, 1, 1024, 0, st, tsum, tilesG);
+  B2_LAUNCH(ctx, scan_apply, (unsigned)tilesG, kScanThreads, 0, st, (const uint32_t*)hist, (const uint32_t*)nullptr, G, 0u, 0u, (const uint32_t*)tsum, offsets, (uint32_t*)nullptr);
+  B2_LAUNCH(ctx, msm_sort_fine_place, max_items, 1024, sizeof(SortFineSmem), st, (const uint2*)ent1, sp, (const uint32_t*)base, (const uint32_t*)item_start, (const uint32_t*)cnt2,
+            (const uint32_t*)offsets, idx);
   return B200ZK_OK;
 }
 
@@ -1266,7 +1351,7 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
     B2_TRY(ensure(ctx, s.run_off, (G + 1) * 4));
     B2_TRY(ensure(ctx, s.tsum, std::max(tiles, (Gc + kScanTile - 1) / kScanTile) * 4));
     B2_TRY(ensure(ctx, s.digits, Mk_max * 4)); B2_TRY(ensure(ctx, s.idx, Mk_max * 4));
-    if (two_level) { B2_TRY(ensure(ctx, s.key, Mk_max * 8)); B2_TRY(ensure(ctx, s.ctab, 2 * (Gc + 1) * 4)); }
+    if (two_level) { B2_TRY(ensure(ctx, s.key, Mk_max * 8)); B2_TRY(ensure(ctx, s.ctab, sort_ctab_bytes(ctx->sm_count))); B2_TRY(ensure(ctx, s.cnt2, sort_cnt2_bytes(Mk_max))); }
   }
   B2_TRY(ensure(ctx, ctx->ws_buckets, S_max * xy));
   B2_TRY(ensure(ctx, ctx->ws_segbucket, S_max * 4));
@@ -1298,7 +1383,7 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
     SortPlan sp;
     const bool tl = two_level && make_sort_plan(nk, pl, ctx->sm_count, &sp);
     if (tl) {
-      B2_TRY(run_two_level_sort(ctx, (const void*)(dsc + lo * 32), nk, flags, pl, sp, hist, offsets, tsum, (uint2*)s.key.p, (uint32_t*)s.ctab.p, idx, st, false));
+      B2_TRY(run_two_level_sort(ctx, (const void*)(dsc + lo * 32), nk, flags, pl, sp, hist, offsets, tsum, (uint2*)s.key.p, (uint32_t*)s.ctab.p, (uint32_t*)s.cnt2.p, idx, st, false));
     } else {
       B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
       const unsigned sgrid = (unsigned)std::min<size_t>((nk + 255) / 256, (size_t)ctx->sm_count * 8);
@@ -1434,14 +1519,15 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   const bool two_level = !legacy_sort_knob() && make_sort_plan(n, pl, ctx->sm_count, &sp);
   if (two_level) {
     B2_TRY(ensure(ctx, ctx->ws_key, M_max * 8));
-    B2_TRY(ensure(ctx, ctx->ws_ctab, (2 * ((size_t)sp.C * sp.NC + 1)) * 4));
+    B2_TRY(ensure(ctx, ctx->ws_ctab, sort_ctab_bytes(ctx->sm_count)));
+    B2_TRY(ensure(ctx, ctx->ws_cnt2, sort_cnt2_bytes(M_max)));
     B2_TRY(ensure(ctx, ctx->ws_blocksums, (std::max(tiles, ((size_t)sp.C * sp.NC + kScanTile - 1) / kScanTile)) * 4));
     tsum = (uint32_t*)ctx->ws_blocksums.p;
   }
   phase_mark(ctx, 0, st);
   nvtxRangePushA("b200zk:msm_sort");
   if (sort_mode != 2 && two_level) {
-    B2_TRY(run_two_level_sort(ctx, d_scalars, n, flags, pl, sp, hist, offsets, tsum, (uint2*)ctx->ws_key.p, (uint32_t*)ctx->ws_ctab.p, idx, st, true));
+    B2_TRY(run_two_level_sort(ctx, d_scalars, n, flags, pl, sp, hist, offsets, tsum, (uint2*)ctx->ws_key.p, (uint32_t*)ctx->ws_ctab.p, (uint32_t*)ctx->ws_cnt2.p, idx, st, true));
   } else if (sort_mode != 2) {
     B2_CUDA(ctx, cudaMemsetAsync(hist, 0, G * 4, st));
     const unsigned sgrid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);

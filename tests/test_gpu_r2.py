@@ -339,3 +339,35 @@ def test_verifier_rejects_non_canonical_encodings(ctx):
         assert ver.verify_batch([proof, forged, proof], [[x], [x], [x + pyref.R]]) == [True, False, False]
     finally:
         prover.close()
+
+
+@pytest.mark.parametrize("table", [False, True])
+def test_two_level_sort_on_skewed_scalars(ctx, table):
+    """The r2 sort (n >= 2^16) under the distributions that break naive bucket sorts: all scalars equal
+    (13 buckets hold everything: one coarse bin per window), half zeros, tiny scalars (only window 0 populated), r - 1, and a
+    Zipf-like mix -- each against the CPU oracle's Pippenger.  The fine pass works on fixed segments of a bin, so a heavy
+    bin costs time, not correctness or one CTA's patience."""
+    n = (1 << 17) + 12345
+    k, d = chain_kd()
+    pts = orc.g1_chain(n, k, d)
+    dp = to_dev(pts)
+    rnd = orc.rand_fr(pyref.SEED_SCALARS, 0, n)
+    cases = {}
+    eq = np.tile(rnd[5], (n, 1)); cases["all equal"] = eq
+    hz = rnd.copy(); hz[::2] = 0; cases["half zeros"] = hz
+    tiny = np.zeros((n, 4), dtype=np.uint64); tiny[:, 0] = rnd[:, 0] & np.uint64(0xFFFF); cases["below 2^16"] = tiny
+    rm1 = np.tile(orc.int_to_limbs(pyref.R - 1), (n, 1)); cases["all r - 1"] = rm1
+    zipf = rnd.copy(); zipf[: n // 2] = rnd[7]; zipf[n // 2: 3 * n // 4] = rnd[11]; cases["zipf-like"] = zipf
+    h = None
+    try:
+        if table:
+            h = ctx.g1_bases_from_device(dp, n)
+            ctx.bases_precompute(h, 0)
+        for name, s in cases.items():
+            s = np.ascontiguousarray(s)
+            exp = orc.g1_msm(pts, s)
+            got = ctx.g1_msm_resident_device(h, to_dev(s), n) if table else ctx.g1_msm_device(dp, to_dev(s), n)
+            assert got == exp, name
+    finally:
+        if h is not None:
+            ctx.bases_free(h)
