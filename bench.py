@@ -46,14 +46,22 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 
 # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) also write to fd 1,
 # so keep a private handle on the real stdout for the result line and point fd 1 at stderr for everything else.
-_RESULT_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
-sys.stdout = sys.stderr
+# Done in main() only: importing bench (tests, tools) leaves the importer's stdout alone.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
 
 
 def emit_result(line: dict):
-    _RESULT_OUT.write(json.dumps(line) + "\n")
-    _RESULT_OUT.flush()
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 SEED_SCALARS, SEED_POINTS, SEED_NTT = 0xB2000001, 0xB2000002, 0xB2000003
@@ -684,6 +692,7 @@ def run_gpu(args):
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -32,6 +32,9 @@ struct NttTables {
   const uint4* ninv;   // n^-1
   const uint4* d16;    // d16[x] = w_{2^16}^x, x < 2^16: inter-pass twiddles of passes with Ns*R <= 2^16 in ONE lookup
   const uint4* lo_n;   // lo_n[x] = lo[x] * n^-1: the last pass of an inverse transform scales through its twiddles
+  const uint4* full;   // last pass with Ns*R = N > 2^16 only, or nullptr: full[(r << log_ns) + jm] = w_N^(r*jm) (* n^-1 when the
+                       // pass folds the scale): ONE streamed lookup and one product per element instead of two lookups and
+                       // two products -- HBM has the room (N * 32 B per table) and the pass the bandwidth (it is product bound)
 };
 static constexpr uint32_t kDirectBits = 16;
 
@@ -97,6 +100,16 @@ __global__ void __launch_bounds__(128) ntt_build_tables(uint32_t log_n, int inve
   store_fe<Fr>(out, id, val);
 }
 
+// full[(r << lns) + jm] = w_N^(r * jm) for r < 2^(k - lns), jm < 2^lns, from the two-level tables (lo_sel = lo or lo * n^-1)
+__global__ void __launch_bounds__(256) ntt_build_full(uint32_t k, uint32_t lns, const uint4* lo_sel, const uint4* hi, void* out) {
+  const size_t n = (size_t)1 << k;
+  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < n; id += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(id >> lns), jm = (uint32_t)id & ((1u << lns) - 1);
+    const uint32_t e = r * jm;  // < 2^k
+    store_fe<Fr>(out, id, Fr::mul(load_fe_nc<Fr>(lo_sel, e & ((1u << kLoBits) - 1)), load_fe_nc<Fr>(hi, e >> kLoBits)));
+  }
+}
+
 // flags[0] = 1 iff g^(2^28) == 1 and g^(2^27) != 1 (g canonical, < r)
 __global__ void ntt_check_root(RootArg g, uint32_t* flags) {
   if (blockIdx.x || threadIdx.x) return;
@@ -143,11 +156,13 @@ B2_D void sts_fr(uint4* sm, uint32_t i, const Fr& a) {
 }
 
 // v * w_{2^L}^(r*jm): one lookup when L <= 16, else two lookups and a product
-B2_D Fr interpass_twiddle(const Fr& v, uint32_t r, uint32_t jm, uint32_t k, uint32_t L, const NttTables& tb, bool scaled) {
+B2_D Fr interpass_twiddle(const Fr& v, uint32_t r, uint32_t jm, uint32_t k, uint32_t lns, uint32_t L, const NttTables& tb, bool scaled) {
   const uint32_t x = r * jm;
   if (!x) return scaled ? Fr::mul(v, load_fe_nc<Fr>(tb.ninv, 0)) : v;
   Fr tw;
-  if (L <= kDirectBits) {  // scaled is only requested for L > 16
+  if (tb.full) {           // only set for the pass it was built for (L == k)
+    tw = load_fe_nc<Fr>(tb.full, ((size_t)r << lns) + jm);
+  } else if (L <= kDirectBits) {  // scaled is only requested for L > 16
     tw = load_fe_nc<Fr>(tb.d16, x << (kDirectBits - L));
   } else {
     uint32_t e = x << (k - L);
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass(PassArgs a) {
   const uint4* stage_tw = a.tb.stage + 2 * ((size_t)(R >> 1) - 1);
   auto first_touch = [&](Fr v, uint32_t row, uint32_t c) -> Fr {
     if (a.coset_in) v = coset_scale(v, (size_t)(j0 + c) + ((size_t)row << stride_log), k, a.c_lo, a.c_hi);  // h^index
-    if (lns) v = interpass_twiddle(v, row, (j0 + c) & ns_mask, k, lns + s, a.tb, a.scale_in != 0);  // w_{2^L}^(row * (j mod Ns))
+    if (lns) v = interpass_twiddle(v, row, (j0 + c) & ns_mask, k, lns, lns + s, a.tb, a.scale_in != 0);  // w_{2^L}^(row * (j mod Ns))
     return v;
   };
   uint32_t q = 0;
@@ -336,6 +351,36 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
   out->ninv = out->hi + 2 * (size_t)n_hi;
   out->d16 = out->ninv + 2;
   out->lo_n = out->d16 + 2 * ((size_t)1 << kDirectBits);
+  out->full = nullptr;
+  return B200ZK_OK;
+}
+
+// The last pass's direct twiddle table (NttTables::full), built on first use per (size, direction, root, last-pass width,
+// scaled).  Largest size: B200ZK_NTT_FULL_TW (default 26 -> 2 GiB per table; 0 disables).  Any failure to allocate leaves
+// *out = nullptr and the pass on the two-level tables: this is an optimisation, never a requirement.
+static int get_full_table(b200zk_ctx* ctx, uint32_t log_n, bool inverse, uint32_t s_last, bool scaled, const NttTables& tb, cudaStream_t st, const uint4** out) {
+  *out = nullptr;
+  static int max_log = -1;
+  if (max_log < 0) { const char* e = getenv("B200ZK_NTT_FULL_TW"); max_log = (e && *e) ? atoi(e) : 26; }
+  if (log_n <= kDirectBits || (int)log_n > max_log || s_last >= log_n) return B200ZK_OK;
+  uint32_t tag[8] = {0xF0117ab1u, log_n, inverse ? 1u : 0u, s_last, scaled ? 1u : 0u, 0, 0, 0};
+  uint64_t key = 0xcbf29ce484222325ull ^ ctx->ntt_root_id;
+  for (int i = 0; i < 5; ++i) key = (key ^ tag[i]) * 0x100000001b3ull;
+  key |= 1ull << 63;
+  auto it = ctx->twiddles.find(key);
+  if (it != ctx->twiddles.end() && (memcmp(it->second.gen, tag, 32) != 0 || memcmp(it->second.root, ctx->ntt_root, 32) != 0)) return B200ZK_OK;  // key collision: do without
+  if (it == ctx->twiddles.end()) {
+    TwiddleSet ts;
+    memcpy(ts.gen, tag, 32);
+    memcpy(ts.root, ctx->ntt_root, 32);
+    ts.bytes = ((size_t)1 << log_n) * 32;
+    if (cudaMalloc(&ts.d, ts.bytes) != cudaSuccess) { cudaGetLastError(); return B200ZK_OK; }
+    B2_LAUNCH(ctx, ntt_build_full, ctx->sm_count * 8, 256, 0, st, log_n, log_n - s_last, scaled ? tb.lo_n : tb.lo, tb.hi, ts.d);
+    if (cudaEventCreateWithFlags(&ts.ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ts.ready, st); else { cudaGetLastError(); ts.ready = nullptr; B2_CUDA(ctx, cudaStreamSynchronize(st)); }
+    it = ctx->twiddles.emplace(key, ts).first;
+  }
+  if (it->second.ready) B2_CUDA(ctx, cudaStreamWaitEvent(st, it->second.ready, 0));
+  *out = (const uint4*)it->second.d;
   return B200ZK_OK;
 }
 
@@ -489,6 +534,7 @@ int ntt_run(b200zk_ctx* ctx, void* d_data, uint32_t log_n, uint32_t flags, const
       a.coset_out = (coset && inverse && p == pl.P - 1) ? 1 : 0;
       a.c_lo = (const uint4*)c_lo; a.c_hi = (const uint4*)c_hi;
       a.tb = tb;
+      if (last && log_ns > 0) B2_TRY(get_full_table(ctx, log_n, inverse, pl.s[p], fold, tb, st, &a.tb.full));
       B2_TRY(launch_pass(ctx, a, st));
       log_ns += pl.s[p];
       if (!in_place) cur ^= 1;
