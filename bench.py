@@ -58,6 +58,36 @@ def claim_stdout():
         sys.stdout = sys.stderr
 
 
+def ntt_products_per_element(log_n: int, full_table_max_log: int = 26) -> float:
+    """Modular products one forward transform spends per element -- the host-side count of csrc/ntt.cu's schedule (default
+    plan of make_ntt_plan; radix-4 rounds whose w^0 twiddles are skipped; one inter-pass product per element when the pass's
+    twiddle comes from one lookup -- L <= 16, or the last pass's direct table -- else two)."""
+    k = log_n
+    if k <= 12:
+        passes = [k]
+    elif k <= 20:
+        passes = [(k + 1) // 2, k - (k + 1) // 2]
+    else:
+        s0 = (k + 2) // 3
+        s1 = (k - s0 + 1) // 2
+        passes = [s0, s1, k - s0 - s1]
+    total, done = 0.0, 0
+    for i, s in enumerate(passes):
+        q = 0
+        if s & 1:  # one radix-2 stage: half a product per element, none for jj = 0
+            total += 0.5 * (1 - 1 / (1 << (s - 1)))
+            q = 1
+        while q < s:  # radix-4 round: 4 products per quad, 1 when jj = 0 (one quad in m/2)
+            m2 = 1 << (s - 2 - q)
+            total += 1 - 0.75 / m2
+            q += 2
+        done += s
+        if i > 0:
+            last = i == len(passes) - 1
+            total += 1 if (done <= 16 or (last and 16 < k <= full_table_max_log)) else 2
+    return total
+
+
 def emit_result(line: dict):
     out = _RESULT_OUT or sys.stdout
     out.write(json.dumps(line) + "\n")
@@ -585,8 +615,8 @@ def run_gpu(args):
                "roofline": {"bound": "hbm", "achieved": ntt_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": ntt_bytes / (fwd_ms / 1e3) / 1e9 / peak,
                             "traffic": (profn["dram_bytes_read"] + profn["dram_bytes_write"]) if profn else None,
-                            "binding_roofline": {"bound": "fmaheavy pipe: ~12 modular products per element", "peak_products_per_s": modmul_peak,
-                                                 "frac": 12 * n / (fwd_ms / 1e3) / modmul_peak,
+                            "binding_roofline": {"bound": "fmaheavy pipe: modular products per element counted from the schedule (at 2^24: 3 passes x 3.0 stage-twiddle products after the trivial ones + 1 inter-pass product in passes 2 and 3 = 11; 12 without the last pass's direct twiddle table)", "peak_products_per_s": modmul_peak,
+                                                 "products_per_element": ntt_products_per_element(log_n, int(os.environ.get("B200ZK_NTT_FULL_TW") or 26)), "frac": ntt_products_per_element(log_n, int(os.environ.get("B200ZK_NTT_FULL_TW") or 26)) * n / (fwd_ms / 1e3) / modmul_peak,
                                                  "ncu_sm__pipe_fmaheavy_cycles_active_pct": (profn.get("fmaheavy_pct") or profn.get("fmaheavy_pct_elapsed")) if profn else None},
                             "note": "whole transform (all passes); algorithmic bytes = 64*n; traffic = sum of the passes' dram bytes (profiles/r2_ncu_kernels.json) or null"}}
         # end to end through the host-buffer C-ABI call: pinned host buffer in, transformed in place, copies included

@@ -1476,6 +1476,10 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   const size_t G = (size_t)pl.Wr * pl.B;
   const size_t tiles = (G + kScanTile - 1) / kScanTile;
   const size_t xy = 4 * FieldBytes<F>::value;
+  static int dense_knob = -1;  // experiment knob, see the bucket reduction below
+  if (dense_knob < 0) { const char* e = getenv("B200ZK_DENSE_TOTALS"); dense_knob = (e && *e == '0') ? 0 : 1; }
+  const bool dense_totals = dense_knob && G >= ((size_t)1 << 14);
+  if (dense_totals) B2_TRY(ensure(ctx, ctx->ws_totals, G * xy));
   B2_TRY(ensure(ctx, ctx->ws_hist, G * 4));
   B2_TRY(ensure(ctx, ctx->ws_offsets, (G + 1) * 4));
   B2_TRY(ensure(ctx, ctx->ws_cursor, G * 4));
@@ -1581,7 +1585,15 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
   }
   phase_mark(ctx, 4, st);
   const size_t chunks = (size_t)pl.Wr * pl.T;
-  B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, seg_off, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  // Bucket totals first, one thread per bucket (full occupancy, every lane busy), then the running sums over dense totals:
+  // bucket_chunk's threads are few (G / chunk) and serial, so every run addition moved out of them shortens the
+  // latency-bound tail (B200ZK_DENSE_TOTALS=0: the fused form, bucket_chunk summing the runs itself).
+  if (dense_totals) {
+    B2_LAUNCH(ctx, bucket_merge<F>, (unsigned)((G + 127) / 128), 128, 0, st, (const void*)ctx->ws_buckets.p, (const uint32_t*)seg_off, (uint32_t)G, 1, ctx->ws_totals.p);
+    B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, (const void*)ctx->ws_totals.p, (const uint32_t*)nullptr, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  } else {
+    B2_LAUNCH(ctx, bucket_chunk<F>, (unsigned)((chunks + 127) / 128), 128, 0, st, ctx->ws_buckets.p, seg_off, pl, ctx->ws_chunkS.p, ctx->ws_chunkV.p);
+  }
   uint32_t chunk_log2 = 0;
   while ((1u << chunk_log2) < pl.chunk) ++chunk_log2;
   if (pl.T >= 64) {

@@ -12,8 +12,9 @@
 //     out[(j div Ns)*Ns*R + (j mod Ns) + q*Ns] = V[q]
 // One CTA owns a tile of 2^t adjacent j, so every global access is a run of 2^t * 32 B, and the R-point
 // transforms of a tile never leave shared memory.  Inter-pass twiddles come from one 2^16-entry table when
-// Ns*R <= 2^16 (a single lookup), else from two 4096-entry tables (w^lo, w^(hi*4096)): one extra
-// multiplication instead of an n/2-entry table streamed from HBM.
+// Ns*R <= 2^16 (a single lookup); the LAST pass of a larger transform streams them from a direct N-entry table
+// (NttTables::full: the pass is bound by products, not by HBM, and one lookup costs one product instead of two);
+// any other pass, and sizes beyond the table's cap, use two 4096-entry tables (w^lo, w^(hi*4096)) and one extra product.
 #include "common.cuh"
 #include "tma.cuh"
 #include <cstdlib>
@@ -195,6 +196,15 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass(PassArgs a) {
       for (uint32_t r = threadIdx.x; r < R; r += THREADS)
         tma::bulk_load(sm + 2 * ((size_t)r << t), src + ((size_t)j0 + ((size_t)r << stride_log)) * 32, cols * 32u, &tile_bar);
     }
+    // while the tile is in flight: pull this tile's slice of the direct twiddle table (R runs of 2^t * 32 B) into L2,
+    // so that the first round's lookups do not pay HBM latency on top of the tile's
+    if (lns && a.tb.full) {
+      const uint8_t* tw = reinterpret_cast<const uint8_t*>(a.tb.full);
+      for (uint32_t r = threadIdx.x; r < R; r += THREADS) {
+        const uint8_t* p = tw + ((((size_t)r << lns) + (j0 & ns_mask)) << 5);
+        for (uint32_t b = 0; b < cols * 32u; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+      }
+    }
     tma::barrier_wait(&tile_bar, 0);
   }
 
@@ -360,8 +370,8 @@ static int get_tables(b200zk_ctx* ctx, uint32_t log_n, bool inverse, cudaStream_
 // *out = nullptr and the pass on the two-level tables: this is an optimisation, never a requirement.
 static int get_full_table(b200zk_ctx* ctx, uint32_t log_n, bool inverse, uint32_t s_last, bool scaled, const NttTables& tb, cudaStream_t st, const uint4** out) {
   *out = nullptr;
-  static int max_log = -1;
-  if (max_log < 0) { const char* e = getenv("B200ZK_NTT_FULL_TW"); max_log = (e && *e) ? atoi(e) : 26; }
+  const char* knob = getenv("B200ZK_NTT_FULL_TW");  // read per call: tests switch it inside one process
+  const int max_log = (knob && *knob) ? atoi(knob) : 26;
   if (log_n <= kDirectBits || (int)log_n > max_log || s_last >= log_n) return B200ZK_OK;
   uint32_t tag[8] = {0xF0117ab1u, log_n, inverse ? 1u : 0u, s_last, scaled ? 1u : 0u, 0, 0, 0};
   uint64_t key = 0xcbf29ce484222325ull ^ ctx->ntt_root_id;

@@ -119,6 +119,18 @@ def test_ntt_medium_vs_oracle(ctx, log_n):
     _ntt_case(ctx, log_n, eb.NTT_INVERSE)
 
 
+@pytest.mark.parametrize("log_n", [17, 18, 21])
+def test_ntt_direct_twiddle_table_all_modes(ctx, log_n, monkeypatch):
+    """Sizes above 2^16 take the last pass's inter-pass twiddles from a direct N-entry table (one lookup, one product), built
+    on first use per (direction, scaled); B200ZK_NTT_FULL_TW=0 keeps the two-level tables.  Both must be the oracle's bytes in
+    every mode (the plain inverse folds n^-1 into the table, the coset inverse must not)."""
+    modes = [(0, None), (eb.NTT_INVERSE, None), (eb.NTT_COSET, None), (eb.NTT_INVERSE | eb.NTT_COSET, None), (eb.NTT_COSET, 7), (eb.NTT_COSET | eb.NTT_INVERSE, pyref.R - 3)]
+    for knob in ("26", "0"):
+        monkeypatch.setenv("B200ZK_NTT_FULL_TW", knob)
+        for flags, gen in modes:
+            _ntt_case(ctx, log_n, flags, coset_gen=gen)
+
+
 def test_ntt_golden_2_12(ctx):
     """config #1: 2^12 forward against the pure-Python fixture (tests/golden/ntt_2_12.npz)."""
     import os
