@@ -1288,6 +1288,12 @@ static int legacy_sort_knob() {
   if (knob < 0) { const char* e = getenv("B200ZK_SORT"); knob = (e && !strcmp(e, "legacy")) ? 1 : 0; }
   return knob;
 }
+// growth ratio of the host-scalar pipeline's chunk sizes (B200ZK_CHUNK_RATIO, read per call: 1 = equal chunks)
+static double chunk_ratio_knob(double dflt) {
+  const char* e = getenv("B200ZK_CHUNK_RATIO");
+  double r = (e && *e) ? atof(e) : dflt;
+  return (r >= 1.0 && r <= 64.0) ? r : dflt;
+}
 // scratch sizes of the two-level sort for up to M_max entries
 static size_t sort_ctab_bytes(int sm_count) { return (2 * ((size_t)kSortMaxBins * (size_t)sm_count + 1) + kSortMaxBins + 1) * 4; }
 static size_t sort_cnt2_bytes(size_t M_max) { return (M_max / kFineSeg + kSortMaxBins + 1) * (size_t)kSortMaxFine * 4; }
@@ -1336,12 +1342,37 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
   const size_t G = (size_t)pl.Wr * pl.B;
   const size_t tiles = (G + kScanTile - 1) / kScanTile;
   const size_t xy = 4 * FieldBytes<F>::value, pt = 2 * FieldBytes<F>::value;
-  size_t chunk = ((n + K - 1) / K + 1023) & ~(size_t)1023;
+  // Chunk k covers points [bnd[k], bnd[k+1]).  With HOST scalars the sizes grow geometrically (ratio r): only the first
+  // chunk's upload is exposed, and chunk k+1 uploads while chunk k computes -- the kernels are ~3.7x slower per point than
+  // the PCIe copy, so a chunk may be ~3x its predecessor and still arrive in time.  Fewer, larger chunks also pay the
+  // per-chunk costs (sort launches, wave tails, bucket_merge over all G buckets) fewer times.  Resident scalars: equal chunks.
+  size_t bnd[kMaxPipelineChunks + 1];
+  uint32_t chunks = 0;
+  {
+    // measured at 2^24 (tools/e2e_sweep.py, profiles/r2_e2e_sweep.jsonl): G1 3 chunks x4 (37.8 ms against 40.2 ms for 4 equal
+    // chunks, 35.9 ms resident), G2 2 chunks x12 (115.7 against 118.7, 112.4 resident): the ratio tracks compute time / copy time
+    const double r = h_scalars ? chunk_ratio_knob(IsFq2<F>::value ? 12.0 : 4.0) : 1.0;
+    double tot = 0, w = 1;
+    for (uint32_t k = 0; k < K; ++k) { tot += w; w *= r; }
+    double cum = 0; w = 1;
+    bnd[0] = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+      cum += w; w *= r;
+      size_t hi = (k == K - 1) ? n : std::min(n, (((size_t)((double)n * (cum / tot))) + 1023) & ~(size_t)1023);
+      if (hi > bnd[chunks]) bnd[++chunks] = hi;  // empty chunks (tiny n) vanish
+    }
+  }
+  size_t chunk = 0;  // the largest chunk sizes the workspaces
+  for (uint32_t k = 0; k < chunks; ++k) chunk = std::max(chunk, bnd[k + 1] - bnd[k]);
   const size_t Mk_max = chunk * pl.W;
   const size_t resident = resident_slices<F>(ctx);
-  const uint32_t L = pick_slice_len(Mk_max, resident);
-  const size_t S_max = Mk_max / L + 1 + G;
-  const size_t slices = (Mk_max + L - 1) / L;
+  uint32_t Lk[kMaxPipelineChunks];  // slice length per chunk: each fills whole waves of resident threads
+  size_t S_max = 0;
+  for (uint32_t k = 0; k < chunks; ++k) {
+    const size_t Mk = (bnd[k + 1] - bnd[k]) * pl.W;
+    Lk[k] = pick_slice_len(Mk, resident);
+    S_max = std::max(S_max, Mk / Lk[k] + 1 + G);
+  }
   SortPlan sp0;
   const bool two_level = !legacy_sort_knob() && make_sort_plan(chunk, pl, ctx->sm_count, &sp0);
   const size_t Gc = (size_t)kSortMaxBins * (size_t)ctx->sm_count;  // upper bound of C * NC for any chunk
@@ -1361,7 +1392,6 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
   if (h_scalars) B2_TRY(ensure(ctx, ctx->ws_scalars, n * 32 + 32));
   const uint8_t* dsc = (const uint8_t*)(h_scalars ? ctx->ws_scalars.p : d_scalars);
   cudaStream_t cs = ctx->stream_sort;  // the copy stream: uploads only
-  const uint32_t chunks = (uint32_t)((n + chunk - 1) / chunk);
   // uploads: all issued up front on the copy stream (they serialise on the one H2D engine in chunk order); the staging
   // buffer may still be read by the previous call's kernels on `st`, so the copy stream first waits for `st`
   if (h_scalars) {
@@ -1369,13 +1399,14 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
     B2_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_in, 0));
     if (chunks > kMaxPipelineChunks) return fail(ctx, B200ZK_ERR_INVALID_ARG, "msm: too many pipeline chunks");
     for (uint32_t k = 0; k < chunks; ++k) {
-      const size_t lo = (size_t)k * chunk, nk = n - lo < chunk ? n - lo : chunk;
+      const size_t lo = bnd[k], nk = bnd[k + 1] - lo;
       B2_CUDA(ctx, cudaMemcpyAsync((void*)(dsc + lo * 32), (const uint8_t*)h_scalars + lo * 32, nk * 32, cudaMemcpyHostToDevice, cs));
       B2_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], cs));
     }
   }
   auto sort_chunk = [&](uint32_t k) -> int {
-    const size_t lo = (size_t)k * chunk, nk = n - lo < chunk ? n - lo : chunk;
+    const size_t lo = bnd[k], nk = bnd[k + 1] - lo;
+    const uint32_t L = Lk[k];
     SortSlot& s = ctx->slot[k & 1];
     uint32_t *hist = (uint32_t*)s.hist.p, *offsets = (uint32_t*)s.offsets.p, *cursor = (uint32_t*)s.cursor.p, *run_off = (uint32_t*)s.run_off.p,
              *tsum = (uint32_t*)s.tsum.p, *digits = (uint32_t*)s.digits.p, *idx = (uint32_t*)s.idx.p;
@@ -1400,7 +1431,9 @@ static int msm_run_pipelined(b200zk_ctx* ctx, const void* d_points, const void* 
     return B200ZK_OK;
   };
   for (uint32_t k = 0; k < chunks; ++k) {
-    const size_t lo = (size_t)k * chunk, nk = n - lo < chunk ? n - lo : chunk;
+    const size_t lo = bnd[k], nk = bnd[k + 1] - lo;
+    const uint32_t L = Lk[k];
+    const size_t slices = (nk * pl.W + L - 1) / L;
     // sort(k) waits for upload k only: with the kernels serialised there is nothing to gain from sorting ahead (measured:
     // sort(k+1) before accumulate(k) stalls the stream on upload k+1 -- 42.0 ms at 2^24 against the order below)
     B2_TRY(sort_chunk(k));
@@ -1461,9 +1494,11 @@ static int msm_run(b200zk_ctx* ctx, const void* d_points, const void* d_scalars,
     // measured on B200 (profiles/r1_probe.md): with scalars already in HBM one shot is as fast as any chunking
     // (40.9 ms vs 40.0-42 ms at 2^24: the accumulation fills the SMs, so the next chunk's sort barely overlaps);
     // with HOST scalars 4 chunks hide most of the 512 MiB upload (50.5 -> 41.9 ms)
-    // chunks of the host-scalar pipeline: 4 measured best at 2^24 (tools/e2e_sweep.py, profiles/r2_e2e_sweep.jsonl: 46.5 / 42.0 /
-    // 40.6 / 40.9 / 41.3 / 43.4 ms for 1 / 2 / 4 / 6 / 8 / 12 chunks against 36.8 ms with resident scalars)
-    uint32_t K = ctx->msm_chunks ? ctx->msm_chunks : ((h_scalars && n >= ((size_t)1 << 22)) ? 4u : 1u);
+    // chunks of the host-scalar pipeline: few and geometrically growing (msm_run_pipelined); with EQUAL chunks 4 was best
+    // (45.5 / 41.3 / 40.2 / 41.4 ms for 1 / 2 / 4 / 8 chunks against 35.8 ms with resident scalars)
+    static int k_knob = -1;  // experiment knob B200ZK_E2E_CHUNKS: default chunk count of the host-scalar pipeline
+    if (k_knob < 0) { const char* e = getenv("B200ZK_E2E_CHUNKS"); k_knob = (e && *e) ? atoi(e) : 0; if (k_knob < 0 || k_knob > 64) k_knob = 0; }
+    uint32_t K = ctx->msm_chunks ? ctx->msm_chunks : ((h_scalars && n >= ((size_t)1 << 22)) ? (k_knob ? (uint32_t)k_knob : (IsFq2<F>::value ? 2u : 3u)) : 1u);
     if (K > 64) K = 64;
     if (sort_mode == 0 && (K > 1 || h_scalars) && !ctx->profiling && ctx->msm_pair_rounds <= 0 && n >= 4096)
       return msm_run_pipelined<F>(ctx, d_points, d_scalars, h_scalars, n, flags, st, d_partial, pl, K);

@@ -371,3 +371,34 @@ def test_two_level_sort_on_skewed_scalars(ctx, table):
     finally:
         if h is not None:
             ctx.bases_free(h)
+
+
+def test_host_scalar_pipeline_with_growing_chunks(ctx, monkeypatch):
+    """b200zk_g1_msm_resident with HOST scalars cuts the points into chunks whose sizes grow geometrically (only the first
+    chunk's upload is exposed; B200ZK_CHUNK_RATIO, default 3; set_msm_chunks = how many).  Every (count, ratio) -- equal
+    chunks, steep growth, more chunks than 1024-point units at the small size -- must return the one-shot bytes, with the
+    two-level sort (chunks >= 2^16 points) and with the legacy one (small chunks), on plain bases and on a window table."""
+    k, d = chain_kd()
+    n = (1 << 18) + 777
+    pts = orc.g1_chain(n, k, d)
+    s = np.ascontiguousarray(orc.rand_fr(pyref.SEED_SCALARS, 0, n))
+    s[: n // 3] = s[3]                       # a heavy bucket per window inside the first chunks
+    exp = orc.g1_msm(pts, s)
+    dp = to_dev(pts)
+    h = ctx.g1_bases_from_device(dp, n)
+    ht = ctx.g1_bases_from_device(dp, n)
+    ctx.bases_precompute(ht, 0)
+    try:
+        assert ctx.g1_msm_resident_device(ht, to_dev(s), n) == exp
+        for chunks in (2, 3, 5):
+            ctx.set_msm_chunks(chunks)
+            for ratio in ("1", "2.5", "3", "8"):
+                monkeypatch.setenv("B200ZK_CHUNK_RATIO", ratio)
+                assert ctx.g1_msm_resident(ht, s, n) == exp, (chunks, ratio, "table")
+                assert ctx.g1_msm_resident(h, s, n) == exp, (chunks, ratio, "plain")
+                m = 5000                      # tiny: most chunks are empty and vanish
+                assert ctx.g1_msm_resident(h, s[:m], m) == orc.g1_msm(pts[:m], s[:m]), (chunks, ratio, "tiny")
+    finally:
+        ctx.set_msm_chunks(0)
+        ctx.bases_free(h)
+        ctx.bases_free(ht)

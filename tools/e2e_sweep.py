@@ -1,4 +1,5 @@
-"""Sweep of the chunk count of the pipelined host-scalar MSM (b200zk_set_msm_chunks): e2e wall time of
+"""Sweep of the chunk count (b200zk_set_msm_chunks) and the chunk growth ratio (B200ZK_CHUNK_RATIO) of the pipelined
+host-scalar MSM: e2e wall time of
 b200zk_g{1,2}_msm_resident at 2^24 with pinned host scalars, resident window tables.  JSON lines."""
 import json
 import os
@@ -41,8 +42,12 @@ def main():
         for _ in range(3):
             dev(h, sc, n)
         resident_ms = (time.perf_counter() - t0) / 3 * 1e3
-        for K in (1, 2, 4, 6, 8, 12, 16):
+        grid = [(K, 1.0) for K in (1, 2, 4, 8)] + [(K, r) for r in (2.0, 3.0, 4.0, 6.0) for K in (2, 3, 4, 5)]
+        if len(sys.argv) > 3:  # explicit grid: "K:ratio,K:ratio,..."
+            grid = [(int(a.split(":")[0]), float(a.split(":")[1])) for a in sys.argv[3].split(",")]
+        for K, ratio in grid:
             ctx.set_msm_chunks(K)
+            os.environ["B200ZK_CHUNK_RATIO"] = str(ratio)  # read per call by the library
             assert host(h, hs, n) == ref
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -50,8 +55,9 @@ def main():
             for _ in range(reps):
                 host(h, hs, n)
             ms = (time.perf_counter() - t0) / reps * 1e3
-            print(json.dumps({"probe": "e2e_chunks", "group": "g2" if g2 else "g1", "log_n": log_n, "chunks": K, "e2e_ms": ms, "resident_ms": resident_ms}), flush=True)
+            print(json.dumps({"probe": "e2e_chunks", "group": "g2" if g2 else "g1", "log_n": log_n, "chunks": K, "ratio": ratio, "e2e_ms": ms, "resident_ms": resident_ms}), flush=True)
         ctx.set_msm_chunks(0)
+        os.environ.pop("B200ZK_CHUNK_RATIO", None)
         ctx.bases_free(h)
         torch.cuda.empty_cache()
     ctx.close()

@@ -20,7 +20,7 @@ assert ctx.g1_msm_resident(h, s, n) == exp                        # table + host
 ctx.bases_free(h)
 p2 = orc.g2_chain(600, k, d)
 assert ctx.g2_msm_device(dev(p2), dev(s[:600]), 600) == orc.g2_msm(p2, s[:600])
-for log_n in (3, 9, 12, 14):
+for log_n in (3, 9, 12, 14, 17):  # 17: the last pass's direct twiddle table (forward, inverse scaled, inverse unscaled)
     a = orc.fr_to_mont(orc.rand_fr(9, 0, 1 << log_n)); da = dev(a)
     ctx.fr_ntt_device(da, log_n, 0)
     assert (da.cpu().numpy().view(np.uint64).reshape(-1, 4) == orc.fr_ntt(a, log_n)).all()
