@@ -35,3 +35,19 @@ def test_reference_arm_line_and_thread_count():
 
 def test_reference_arm_is_silent_on_other_ranks():
     assert _run({"RANK": "1", "WORLD_SIZE": "2"}).strip() == ""
+
+
+def test_importing_bench_leaves_stdout_alone_and_counts_ntt_products(capsys):
+    """Tools and tests import bench for source_hash() / the product count: the import must not redirect the importer's
+    stdout (only main() claims it), and the NTT product model must follow csrc/ntt.cu's schedule: three 8-stage passes at
+    2^24 = 3 x 3.0 stage products + one inter-pass product in passes 2 and 3 with the last pass's direct table, two there
+    without it; 2^26 exceeds one lookup in its second pass."""
+    sys.path.insert(0, ROOT)
+    import bench
+    print("still here")
+    assert capsys.readouterr().out == "still here\n"
+    assert abs(bench.ntt_products_per_element(24) - 11.012) < 1e-2
+    assert abs(bench.ntt_products_per_element(24, 0) - 12.012) < 1e-2
+    assert abs(bench.ntt_products_per_element(16) - 7.008) < 1e-2           # (8, 8): one lookup, no table needed
+    assert bench.ntt_products_per_element(26) > bench.ntt_products_per_element(24) + 1.9
+    assert len(bench.source_hash()) == 16
