@@ -2,7 +2,7 @@
 samples, the stall reasons summed over the kernel, and the SASS lines where warps wait longest.
     ncu --set full --import-source on --clock-control none -k regex:"^msm_accumulate$" -s 1 -c 1 -o acc python tools/profile_workload.py 22 g1
     ncu -i acc.ncu-rep --page source --csv | gzip -9 > profiles/r2_ncu_source_accumulate.csv.gz
-    python tools/ncu_source_digest.py profiles/r2_ncu_source_accumulate.csv.gz > profiles/r2_ncu_source_accumulate.md"""
+    python tools/ncu_source_digest.py profiles/r2_ncu_source_accumulate.csv.gz "<workload>" "<reading>" > profiles/r2_ncu_source_accumulate.md"""
 import collections
 import csv
 import gzip
@@ -38,7 +38,7 @@ ex, sa, ni = collections.Counter(), collections.Counter(), collections.Counter()
 for r in data:
     o = opcode(r[ix["Source"]])
     ex[o] += f(r, "Instructions Executed"); sa[o] += f(r, "# Samples"); ni[o] += f(r, "Warp Stall Sampling (Not-issued Samples)")
-print(f"# ncu source page of `{kernel.split('(const')[0].replace('void ', '').replace('b200zk::', '')}` (2²² points, window table c = 20; `tools/ncu_source_digest.py`)\n")
+print(f"# ncu source page of `{kernel.split('(const')[0].replace('void ', '').replace('b200zk::', '')}` ({sys.argv[2] if len(sys.argv) > 2 else 'workload not stated'}; `tools/ncu_source_digest.py`)\n")
 print(f"{len(data)} SASS lines, {tot_i:.3e} warp instructions executed, {int(tot_s)} warp-state samples of which {int(tot_n)} ({100 * tot_n / tot_s:.1f} %) fell in cycles where the")
 print("scheduler issued nothing. The full per-line table (stall reasons, L2 sectors, divergence) is the `.csv.gz` next to this file.\n")
 print("| opcode | share of executed instructions | share of all samples | share of not-issued samples |")
@@ -56,7 +56,5 @@ print("\n| SASS line (offset) | instruction | samples | not-issued samples | tim
 print("|---|---|---|---|---|")
 for r in sorted(data, key=lambda r: -f(r, "Warp Stall Sampling (Not-issued Samples)"))[:10]:
     print(f"| `{r[ix['Address']][-5:]}` | `{r[ix['Source']].strip()[:64]}` | {int(f(r, '# Samples'))} | {int(f(r, 'Warp Stall Sampling (Not-issued Samples)'))} | {int(f(r, 'Instructions Executed'))} |")
-print("\nReading: 63 % of all warp samples sit on `IMAD.WIDE` (52 % of the instructions), and the states are the multiplier pipe's own --")
-print("`wait` (the fixed latency between dependent carry-chain steps), `math` (pipe throttle), `dispatch`, `selected` -- while memory")
-print("(`long_sb`) is 3.9 %: the two hottest lines are the consumers of the prefetched index word and of the next bucket offset, i.e. the")
-print("gather latency the software prefetch does not fully hide. Nothing here points at anything but fewer wide multiplies per addition.")
+if len(sys.argv) > 3:
+    print("\nReading: " + sys.argv[3])
